@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""Headline benchmark: exact top-100 angular kNN queries/s over 50,000 samples x 3000
+features, 4096-query batches (BASELINE.json configs[2]) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one batch of 4096 queries answered exactly (ids + distances) against the
+HBM-resident sample matrix.  N > 1 (torchrun, one rank per GPU): every rank holds the
+50k-row matrix and answers its own 4096-query batch -- queries are independent, so
+there is no data-path collective; per-GPU work is fixed (weak scaling) and `value`
+is all ranks' queries / max-over-ranks device time.  `--rows-sharded` runs the other
+multi-GPU mode instead (rows split across ranks, NCCL all-gather + merge of top-k).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SAMPLES, DIM, N_QUERIES, K = 50000, 3000, 4096, 100
+METRIC = "exact kNN queries/s (50k samples x 3000 feats, k=100)"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                     "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80, "sync_boost": 0x10}
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for name, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as exc:      # NVML absent: report that instead of clocks
+            self.reasons.add("nvml_unavailable:%s" % type(exc).__name__)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def synth_matrix(torch, device, n, dim, seed):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    return torch.randn((n, dim), generator=g, device=device, dtype=torch.float32)
+
+
+def cpu_baseline_run(n_samples, dim, k, n_queries, threads, seed=1234):
+    """Times the C port of exact_search_nn (oracle/oracle.c) on `n_queries` queries of the
+    same workload, queries split over `threads` host threads.  Returns queries/s."""
+    from oracle import c_oracle
+    c_oracle.build()
+    rng = np.random.default_rng(seed)
+    S = rng.standard_normal((n_samples, dim), dtype=np.float32)
+    rows = rng.permutation(n_samples)[:n_queries]
+    Q = S[rows].astype(np.float64)
+    t0 = time.perf_counter()
+    ids, _ = c_oracle.exact_search_batch(S, Q, k, n_threads=threads)
+    dt = time.perf_counter() - t0
+    assert np.array_equal(ids[:, 0], rows.astype(np.int32))      # each query finds itself first
+    return n_queries / dt, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (C port of morna.py:681-712, the
+    reference itself is Python 2 and cannot run here) on all host cores."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = 2 * cores
+    for _ in range(args.warmup):
+        cpu_baseline_run(N_SAMPLES, DIM, K, min(per_step, cores), cores)
+    t_total, q_total = 0.0, 0
+    for _ in range(args.steps):
+        _, dt = cpu_baseline_run(N_SAMPLES, DIM, K, per_step, cores)
+        t_total += dt
+        q_total += per_step
+    value = q_total / t_total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "50000 samples x 3000 features, exact top-100, %d-query sample per step "
+                                   "(of the 4096-query batch)" % per_step},
+            "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
+                             "sample": "%d queries/step x %d steps, C port of exact_search_nn, one thread per core" % (per_step, args.steps)},
+            "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows-sharded", action="store_true", help="split rows across ranks + NCCL top-k merge")
+    ap.add_argument("--samples", type=int, default=N_SAMPLES)
+    ap.add_argument("--queries", type=int, default=N_QUERIES)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as td
+    from morna_b200 import _lib, dist as mdist
+    from morna_b200.search import MornaSearch
+    _lib.require_cuda()
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        td.init_process_group("nccl", device_id=device)
+    lib = _lib.load()
+    n_samples, nq = args.samples, args.queries
+
+    # ---- synthetic index, resident in HBM
+    if args.rows_sharded and world > 1:
+        lo, hi = mdist.shard_bounds(n_samples, rank, world)
+        S = synth_matrix(torch, device, hi - lo, DIM, 1234 + rank)
+        srch = MornaSearch(vectors=S, stats=(n_samples, hi - lo, DIM), device=device)
+        srch.row_lo, srch.row_hi = lo, hi                   # global ids of this block
+        qgen = torch.Generator(device=device); qgen.manual_seed(99)
+        queries64 = torch.randn((nq, DIM), generator=qgen, device=device, dtype=torch.float32).to(torch.float64)
+    else:
+        S = synth_matrix(torch, device, n_samples, DIM, 1234)
+        srch = MornaSearch(vectors=S, stats=(n_samples, n_samples, DIM), device=device)
+        qg = torch.Generator(device="cpu"); qg.manual_seed(99 + rank)
+        rows = torch.randperm(n_samples, generator=qg)[:nq].to(device)
+        queries64 = S[rows].to(torch.float64)               # in-index queries (float32-valued)
+    del S
+    host_q = queries64.cpu().pin_memory()
+    host_ids = torch.empty((nq, K), dtype=torch.int32).pin_memory()
+    host_d = torch.empty((nq, K), dtype=torch.float64).pin_memory()
+
+    def step_resident():
+        ids, d = srch.exact_search_device(queries64, K)
+        if args.rows_sharded and world > 1:
+            ids, d = mdist.all_gather_topk(ids, d)
+            ids, d = mdist.merge_topk(ids, d, K)
+        return ids, d
+
+    def step_e2e():
+        q = host_q.to(device, non_blocking=True)
+        ids, d = srch.exact_search_device(q, K)
+        if args.rows_sharded and world > 1:
+            ids, d = mdist.all_gather_topk(ids, d)
+            ids, d = mdist.merge_topk(ids, d, K)
+        host_ids.copy_(ids, non_blocking=True)
+        host_d.copy_(d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        ids, d = step_resident()
+    torch.cuda.synchronize()
+    if not (args.rows_sharded and world > 1):
+        assert torch.equal(ids[:, 0].long(), rows), "every in-index query must find itself first"
+        assert float(d[:, 0].abs().max()) == 0.0
+
+    # ---- timed region: K steps, inputs resident, CUDA events, max over ranks
+    sampler = ClockSampler(local_rank); sampler.start()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    ms_total = float(t.item())
+    job_queries = nq * (1 if (args.rows_sharded and world > 1) else world)
+    value = job_queries * args.steps / (ms_total / 1e3)
+
+    # ---- end to end through the host API: pinned host queries in, host results out
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    e2e_value = job_queries * args.steps / float(t.item())
+
+    # ---- dominant kernel alone, CUDA events on its stream
+    peaks = measured_peaks()
+    roofline = dominant_kernel_roofline(torch, lib, _lib, srch, queries64, peaks)
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            nq_cpu = 4 * cores
+            v, dt = cpu_baseline_run(N_SAMPLES, DIM, K, nq_cpu, cores)
+            cpu = {"value": v, "unit": "queries/s", "cores": cores, "kind": "port",
+                   "sample": "%d of the 4096 queries, C port of exact_search_nn (morna.py:681-712), %d threads, %.1f s"
+                             % (nq_cpu, cores, dt)}
+        line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": roofline.pop("dtype"), "data": "synthetic",
+                "config": {"workload": "%d samples x %d features (gaussian, seed 1234), %d in-index queries per GPU "
+                                       "per step, exact top-%d ids+distances" % (n_samples, DIM, nq, K),
+                           "parallelism": ("rows-sharded x%d + NCCL all-gather merge" % world) if args.rows_sharded
+                                          else ("replicated index, queries sharded x%d" % world),
+                           "l2": "inputs larger than L2 (sample matrix %.0f MB)" % (n_samples * DIM * 4 / 1e6)},
+                "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(host_q.numel() * 8),
+                        "d2h_bytes_per_step": int(host_ids.numel() * 4 + host_d.numel() * 8)},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "peaks": peaks["source"]}
+        print(json.dumps(line))
+    if world > 1:
+        td.destroy_process_group()
+
+
+def dominant_kernel_roofline(torch, lib, _lib, srch, queries64, peaks):
+    """Times the dominant kernel of the step by itself (CUDA events on the launching
+    stream).  Until the tcgen05 contraction lands this is the FP64 distance scan."""
+    nq = min(queries64.shape[0], 512)
+    n = srch.row_hi - srch.row_lo
+    dist = torch.empty((nq, n), dtype=torch.float64, device=srch.device)
+    call = lambda: _lib.check(lib.morna_angular_distances(
+        _lib.dev_ptr(srch.vectors), _lib.dev_ptr(srch.pp), n, srch.dim, srch.ld, _lib.dev_ptr(queries64), nq,
+        queries64.stride(0), _lib.dev_ptr(dist), n, _lib.stream_ptr()), "morna_angular_distances")
+    for _ in range(3):
+        call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * nq * n * srch.dim
+    achieved = flops / (ms / 1e3) / 1e12
+    peak = peaks["bf16_tflops"]
+    return {"bound": "tensor", "kernel": "angular_distances_kernel<4> (FP64 SIMT scan; tensor-core pass not built yet)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "algorithmic": "2*Q*N*D flops, Q=%d N=%d D=%d per launch" % (nq, n, srch.dim),
+            "launch_ms": ms, "peak_source": peaks["source"] + " bf16 burst", "dtype": "f64"}
+
+
+if __name__ == "__main__":
+    main()

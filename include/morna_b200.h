@@ -1,0 +1,158 @@
+/* morna_b200 -- C ABI of the B200-native replacement for morna's hot path.
+ *
+ * The reference (commanderson/morna, Python 2) has no FFI of its own: its only
+ * native boundaries on this path are the third-party wheels `mmh3` and `annoy`
+ * and the pure-Python loops around them.  Each entry point below names the
+ * reference lines (morna.py) whose work it takes over.  A maintainer binds this
+ * header from Python with ctypes; the in-repo binding is
+ * morna_b200/_lib.py.
+ *
+ * Conventions
+ *   - extern "C"; every function returns an int status: 0 = MORNA_OK, < 0 = error
+ *     (morna_status_string() names it).  Nothing throws, exits or prints.
+ *   - Pointers marked [dev] are device pointers owned by the caller (for example a
+ *     torch tensor's data_ptr()); [host] are host pointers.  The library never
+ *     allocates device memory: scratch space is a caller-provided workspace whose
+ *     size the matching *_workspace_bytes() function reports.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *     the call returns without synchronising unless stated otherwise.
+ *   - No global mutable state: calls on different streams / threads are independent.
+ *   - Row-major matrices carry an explicit leading dimension `ld` in elements.
+ *     Sample vectors: float32, ld % 4 == 0, pad columns [dim, ld) must be zero.
+ */
+#ifndef MORNA_B200_H
+#define MORNA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MORNA_ABI_VERSION 1
+
+enum {
+    MORNA_OK = 0,
+    MORNA_ERR_INVALID_ARGUMENT = -1,
+    MORNA_ERR_WORKSPACE_TOO_SMALL = -2,
+    MORNA_ERR_CUDA = -3,          /* a CUDA runtime/driver call failed; see morna_last_cuda_error() */
+    MORNA_ERR_UNSUPPORTED_DEVICE = -4, /* not an sm_100 device */
+    MORNA_ERR_NO_SAMPLES = -5,    /* morna.py:399-403: no internal ids were assigned */
+    MORNA_ERR_CAPACITY = -6       /* an output list overflowed its caller-provided capacity */
+};
+
+int morna_abi_version(void);
+const char *morna_status_string(int status);
+/* last CUDA error code seen by the calling thread inside this library (0 = none) */
+int morna_last_cuda_error(void);
+/* number of kernels this library has launched from the calling process (monotone counter) */
+int64_t morna_kernel_launch_count(void);
+/* sm count / compute capability of the current device */
+int morna_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor);
+
+/* ------------------------------------------------------------------ index build */
+
+/* Feature-hash J junction keys.  Replaces mmh3.hash + sign + floor-mod at
+ * morna.py:369-371 (and :625-627 for queries).
+ *   keys    [dev] packed key bytes ("chr start end", ASCII, no terminators)
+ *   key_off [dev] int32[J+1] byte offsets into keys
+ *   raw     [dev] int32[J]  MurmurHash3_x86_32(key, seed 0) as signed int32
+ *   bucket  [dev] int32[J]  raw mod dim, Python floor-mod (always in [0, dim))
+ *   sign    [dev] int8[J]   -1 if raw < 0 else +1
+ */
+int morna_hash_junctions(const uint8_t *keys, const int32_t *key_off, int64_t n_rows,
+                         int32_t dim, int32_t *raw, int32_t *bucket, int8_t *sign,
+                         void *stream);
+
+/* Per-row idf on the HOST with the C library's log(), i.e. the very function
+ * CPython's math.log calls: idf[j] = log((double)sample_count / running_freq[j]),
+ * 0 where pass[j] == 0.  Replaces morna.py:372-374.  All pointers [host]. */
+int morna_idf_host(const int64_t *running_freq, const uint8_t *pass, int64_t n_rows,
+                   int64_t sample_count, double *idf);
+
+/* First-seen internal ids.  Replaces the try/except at morna.py:377-382: scanning
+ * passing rows in file order and each row's sample list left to right, the i-th
+ * distinct sample id met gets internal id i.
+ *   row_off      [dev] int64[J+1] CSR offsets into sample[]
+ *   pass         [dev] uint8[J]   1 if len(samples) >= sample_threshold (morna.py:361)
+ *   sample       [dev] int32[nnz] sample ids, each in [0, max_sample_id]
+ *   id_of_sample [dev] int32[max_sample_id+1] out: internal id or -1
+ *   n_kept       [dev] int32[1]   out: number of ids assigned (.stats.mor line 2)
+ */
+size_t morna_assign_internal_ids_workspace_bytes(int64_t n_rows, int64_t nnz, int32_t max_sample_id);
+int morna_assign_internal_ids(const int64_t *row_off, const uint8_t *pass, int64_t n_rows,
+                              const int32_t *sample, int64_t nnz, int32_t max_sample_id,
+                              int32_t *id_of_sample, int32_t *n_kept,
+                              void *workspace, size_t workspace_bytes, void *stream);
+
+/* Scatter-add of sign * (coverage * idf) into per-sample vectors.  Replaces the
+ * per-pair loop at morna.py:376-388.  Sums are double and every (sample, bucket)
+ * cell is accumulated in file row order, so cells equal the reference's Python
+ * floats bit for bit (when a row does not list the same sample twice).
+ * The accumulator is bucket-major: acc[b * acc_ld + (internal_id - id_lo)], and
+ * only internal ids in [id_lo, id_hi) are accumulated (multi-GPU shards by id
+ * range, each rank streaming the same rows).  The call zero-fills acc itself.
+ *   bucket/sign/idf  [dev] per-row, from morna_hash_junctions / morna_idf_host
+ *   cov              [dev] int32[nnz] coverages
+ *   acc              [dev] double[dim * acc_ld], acc_ld >= id_hi - id_lo
+ */
+size_t morna_index_accumulate_workspace_bytes(int64_t n_rows, int32_t dim);
+int morna_index_accumulate(const int64_t *row_off, const uint8_t *pass, const int32_t *bucket,
+                           const int8_t *sign, const double *idf, int64_t n_rows,
+                           const int32_t *sample, const int32_t *cov, int64_t nnz,
+                           const int32_t *id_of_sample, int32_t id_lo, int32_t id_hi,
+                           int32_t dim, double *acc, int64_t acc_ld,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
+/* Round the double accumulator to the float32 sample matrix, row = internal id.
+ * Replaces Annoy add_item's float cast at morna.py:405-407 / 422-424.
+ *   vectors [dev] float32[n_ids * ld], pad columns zero-filled by this call */
+int morna_round_store(const double *acc, int64_t acc_ld, int32_t n_ids, int32_t dim,
+                      float *vectors, int64_t ld, void *stream);
+
+/* ------------------------------------------------------------------ exact search */
+
+/* Per-row squared norms pp[i] = sum_j v[i][j]^2 in double, with the same
+ * summation tree the distance kernels use for pq and qq (so a stored row queried
+ * against itself is at distance exactly 0, as in the reference).  Part of
+ * cosine_distance, morna.py:101-108, hoisted out of the per-query loop.
+ *   pp [dev] double[n] */
+int morna_row_norms(const float *vectors, int64_t n, int32_t dim, int64_t ld, double *pp,
+                    void *stream);
+
+/* Exact angular distances of nq queries to n stored rows:
+ *   d = sqrt(max(0, 2 - 2*pq/sqrt(pp*qq))) if pp*qq > 0 else sqrt(2)
+ * with pp, qq, pq accumulated in double over float32-valued rows -- morna.py:101-114
+ * (the reference leaves a rounding-negative radicand unclamped and would raise).
+ *   queries [dev] double[nq * q_ld]  (q_ld >= dim)
+ *   dist    [dev] double[nq * dist_ld]
+ */
+int morna_angular_distances(const float *vectors, const double *pp, int64_t n, int32_t dim,
+                            int64_t ld, const double *queries, int64_t nq, int64_t q_ld,
+                            double *dist, int64_t dist_ld, void *stream);
+
+/* Exact top-k of each of nq key lists under the reference's order
+ * (morna.py:705-712): distance ascending, equal distances by id DESCENDING.
+ *   keys   [dev] double[nq * key_ld]      (n valid entries per list)
+ *   ids    [dev] int32[nq * key_ld] or NULL; NULL means id = id_base + position
+ *   out_ids/out_dist [dev] [nq * k]; lists shorter than k are padded with id -1, +inf
+ */
+size_t morna_select_topk_workspace_bytes(int64_t n, int64_t nq, int32_t k);
+int morna_select_topk(const double *keys, const int32_t *ids, int64_t n, int64_t key_ld,
+                      int32_t id_base, int64_t nq, int32_t k,
+                      int32_t *out_ids, double *out_dist,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* exact_search_nn for nq queries in one call (morna.py:681-712): distances + top-k.
+ * Internally tiles the queries so the distance scratch stays bounded. */
+size_t morna_knn_exact_workspace_bytes(int64_t n, int64_t nq, int32_t k);
+int morna_knn_exact(const float *vectors, const double *pp, int64_t n, int32_t dim, int64_t ld,
+                    int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
+                    int32_t *out_ids, double *out_dist,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MORNA_B200_H */

@@ -1,0 +1,67 @@
+"""Multi-GPU exact search: the sample matrix is row-sharded (row = internal id) in
+contiguous blocks, one process per GPU; every rank answers the replicated queries
+on its block, the per-rank top-k lists are all-gathered (NCCL over NVLink; gloo in
+CPU tests) and merged under the reference order.  The union of per-shard exact
+top-k lists contains the global top-k, so the result equals one process scanning
+all rows (morna.py:697-712).  This is the only exchange step on the path.
+"""
+import torch
+
+from . import _lib
+
+
+def shard_bounds(n_rows, rank, world):
+    """Contiguous block [lo, hi) of rank `rank`: ceil(n/world) rows per rank."""
+    per = -(-n_rows // world)
+    lo = min(rank * per, n_rows)
+    return lo, min(lo + per, n_rows)
+
+
+def merge_topk(ids, dists, k, stream=None):
+    """Exact top-k of concatenated candidate lists.  ids int32 [nq x m], dists float64
+    [nq x m] on the GPU; entries with id < 0 are padding.  Order: distance ascending,
+    equal distances id descending (morna.py:705-712)."""
+    lib = _lib.load()
+    assert ids.is_cuda and dists.is_cuda and ids.shape == dists.shape
+    ids = ids.contiguous().to(torch.int32)
+    dists = dists.contiguous().to(torch.float64)
+    nq, m = ids.shape
+    out_i = torch.empty((nq, k), dtype=torch.int32, device=ids.device)
+    out_d = torch.empty((nq, k), dtype=torch.float64, device=ids.device)
+    if nq == 0:
+        return out_i, out_d
+    with torch.cuda.device(ids.device):
+        ws = _lib.workspace(lib.morna_select_topk_workspace_bytes(m, nq, k), ids.device)
+        done = 0
+        while done < nq:                     # grid.y limit of the select kernel
+            cnt = min(nq - done, 65535)
+            _lib.check(lib.morna_select_topk(_lib.dev_ptr(dists[done:]), _lib.dev_ptr(ids[done:]), m, m, 0, cnt, k,
+                                             _lib.dev_ptr(out_i[done:]), _lib.dev_ptr(out_d[done:]),
+                                             _lib.dev_ptr(ws), ws.numel(), _lib.stream_ptr(stream)),
+                       "morna_select_topk")
+            done += cnt
+    return out_i, out_d
+
+
+def all_gather_topk(ids, dists, group=None):
+    """Gather every rank's [nq x k] lists -> [nq x world*k], rank-major along dim 1."""
+    import torch.distributed as td
+    world = td.get_world_size(group)
+    if world == 1:
+        return ids, dists
+    gi = [torch.empty_like(ids) for _ in range(world)]
+    gd = [torch.empty_like(dists) for _ in range(world)]
+    td.all_gather(gi, ids.contiguous(), group=group)
+    td.all_gather(gd, dists.contiguous(), group=group)
+    return torch.cat(gi, dim=1), torch.cat(gd, dim=1)
+
+
+def sharded_exact_search(local_search, queries, k, group=None, merge=merge_topk):
+    """`local_search(queries, k)` -> this rank's (ids, dists) with GLOBAL internal ids.
+    Returns the merged global (ids, dists), identical on every rank."""
+    ids, dists = local_search(queries, k)
+    ids, dists = all_gather_topk(ids, dists, group)
+    import torch.distributed as td
+    if td.is_available() and td.is_initialized() and td.get_world_size(group) > 1:
+        return merge(ids, dists, k)
+    return ids, dists

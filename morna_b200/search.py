@@ -1,0 +1,196 @@
+"""MornaSearch -- host-side mirror of the reference class (morna.py:522-787) with the
+exact scan running on the B200.  Loads basename.stats/.freq/.map.mor and the vector
+store, keeps the float32 sample matrix resident in HBM, and answers exact angular
+top-k queries under the reference's order (distance ascending, ties id-descending).
+"""
+import math
+import os
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+from . import _lib, files
+from .index import round_up
+
+
+class MornaSearch(object):
+    def __init__(self, basename=None, device=None, shard=None, vectors=None, stats=None,
+                 sample_frequencies=None, internal_id_map=None):
+        """``basename``: index files to load (morna.py:530-550).  ``shard=(rank, world)``
+        keeps only this rank's contiguous block of rows (row = internal id).
+        Alternatively pass ``vectors`` (numpy/torch [n x dim] float32) and ``stats``
+        = (sample_count, index_size, dim) directly."""
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.basename = basename
+        if basename is not None:
+            self.sample_count, self.index_size, self.dim = files.read_stats(basename)
+            self.sample_frequencies = files.read_freq(basename)
+            self.internal_id_map = files.read_map(basename)
+            if os.path.exists(basename + ".vec.mor"):
+                host = files.read_vectors(basename)
+            elif os.path.exists(basename + ".annoy.mor"):
+                host = files.read_annoy_item_vectors(basename + ".annoy.mor", self.index_size, self.dim)
+            else:
+                raise IOError("no vector store for index " + basename)
+        else:
+            self.sample_count, self.index_size, self.dim = stats
+            self.sample_frequencies = sample_frequencies if sample_frequencies is not None else defaultdict(int)
+            self.internal_id_map = internal_id_map if internal_id_map is not None else {}
+            host = vectors
+        if host.shape != (self.index_size, self.dim):
+            raise ValueError("vector store shape %r does not match stats %r"
+                             % (tuple(host.shape), (self.index_size, self.dim)))
+        rank, world = shard if shard is not None else (0, 1)
+        per = -(-self.index_size // world)
+        self.row_lo = min(rank * per, self.index_size)
+        self.row_hi = min(self.row_lo + per, self.index_size)
+        self.ld = round_up(self.dim, 4)
+        self._load_rows(host)
+        self.query = defaultdict(int)                      # morna.py:540
+        self.query_sample = [0.0] * self.dim               # :541
+        self._ws = None
+
+    def _load_rows(self, host):
+        n = self.row_hi - self.row_lo
+        dev = self.device
+        self.vectors = torch.zeros((n, self.ld), dtype=torch.float32, device=dev)
+        if n:
+            if isinstance(host, torch.Tensor):
+                block = host[self.row_lo:self.row_hi].to(torch.float32)
+            else:
+                block = torch.from_numpy(np.ascontiguousarray(host[self.row_lo:self.row_hi], dtype=np.float32))
+            self.vectors[:, :self.dim].copy_(block, non_blocking=False)
+        self.pp = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.morna_row_norms(_lib.dev_ptr(self.vectors), n, self.dim, self.ld,
+                                                _lib.dev_ptr(self.pp), _lib.stream_ptr()), "morna_row_norms")
+
+    # ------------------------------------------------------------------ query construction
+    def inverse_lookup(self, internal_id):
+        """morna.py:554-572."""
+        match, found = None, False
+        for sample_id, iid in self.internal_id_map.items():
+            if iid == internal_id:
+                if found:
+                    raise RuntimeError(str(internal_id) + " does not have unique mapping in self.internal_id_map.")
+                match, found = sample_id, True
+        return match
+
+    def update_query(self, junction):
+        """morna.py:597-607."""
+        self.query[tuple(junction[:3])] += int(junction[3])
+
+    def hash_keys(self, keys):
+        """Device feature hashing of a list of key strings -> (raw, bucket, sign) numpy."""
+        blobs = [k.encode("utf-8") for k in keys]
+        n = len(blobs)
+        if n == 0:
+            return np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int8)
+        off = np.zeros(n + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(b) for b in blobs])
+        packed = np.frombuffer(b"".join(blobs) + b"\0", dtype=np.uint8).copy()
+        dev = self.device
+        with torch.cuda.device(dev):
+            d_keys, d_off = torch.from_numpy(packed).to(dev), torch.from_numpy(off).to(dev)
+            raw = torch.empty(n, dtype=torch.int32, device=dev)
+            bucket = torch.empty(n, dtype=torch.int32, device=dev)
+            sign = torch.empty(n, dtype=torch.int8, device=dev)
+            _lib.check(self.lib.morna_hash_junctions(_lib.dev_ptr(d_keys), _lib.dev_ptr(d_off), n, self.dim,
+                                                     _lib.dev_ptr(raw), _lib.dev_ptr(bucket), _lib.dev_ptr(sign),
+                                                     _lib.stream_ptr()), "morna_hash_junctions")
+            return raw.cpu().numpy(), bucket.cpu().numpy(), sign.cpu().numpy()
+
+    def finalize_query(self):
+        """morna.py:609-629: hashed, idf-weighted, signed accumulation of the query
+        junctions into ``query_sample`` (Python floats, dictionary order)."""
+        self.query_sample = [0.0] * self.dim
+        junctions = list(self.query.keys())
+        keys = [" ".join(str(t) for t in j) for j in junctions]
+        _, bucket, sign = self.hash_keys(keys)
+        for j, key, b, s in zip(junctions, keys, bucket.tolist(), sign.tolist()):
+            freq = self.sample_frequencies[key]             # defaultdict: inserts 0 like the reference (:619)
+            idf = 0 if freq == 0 else math.log(float(self.sample_count) / freq)
+            self.query_sample[b] += s * (self.query[j] * idf)
+
+    # ------------------------------------------------------------------ exact search
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = _lib.workspace(nbytes, self.device)
+        return self._ws
+
+    def exact_search_device(self, queries, k, stream=None):
+        """queries: CUDA float64 [nq x dim] (row stride = queries.stride(0)).  Returns
+        device (ids int32 [nq x k], dists float64 [nq x k]); ids are global internal
+        ids (row_lo + local row); short lists are padded with id -1 / +inf."""
+        assert queries.is_cuda and queries.dtype == torch.float64 and queries.stride(1) == 1
+        nq = queries.shape[0]
+        n = self.row_hi - self.row_lo
+        dev = self.device
+        out_ids = torch.full((nq, k), -1, dtype=torch.int32, device=dev)
+        out_d = torch.full((nq, k), float("inf"), dtype=torch.float64, device=dev)
+        if n == 0 or nq == 0:
+            return out_ids, out_d
+        with torch.cuda.device(dev):
+            ws = self._workspace(self.lib.morna_knn_exact_workspace_bytes(n, nq, k))
+            _lib.check(self.lib.morna_knn_exact(
+                _lib.dev_ptr(self.vectors), _lib.dev_ptr(self.pp), n, self.dim, self.ld, self.row_lo,
+                _lib.ptr(queries), nq, queries.stride(0), k, _lib.dev_ptr(out_ids), _lib.dev_ptr(out_d),
+                _lib.dev_ptr(ws), ws.numel(), _lib.stream_ptr(stream)), "morna_knn_exact")
+        return out_ids, out_d
+
+    def exact_search_batch(self, queries, k):
+        """Host entry: queries numpy [nq x dim] (float32 or float64) -> numpy (ids, dists)."""
+        q = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float64))
+        if q.numel():
+            q = q.pin_memory()
+        ids, d = self.exact_search_device(q.to(self.device, non_blocking=True), k)
+        return ids.cpu().numpy(), d.cpu().numpy()
+
+    def exact_search_nn(self, num_neighbors, include_distances=True, meta_db=False):
+        """morna.py:681-730 for the current ``query_sample``."""
+        ids, d = self.exact_search_batch(np.asarray(self.query_sample, dtype=np.float64)[None, :], num_neighbors)
+        keep = ids[0] >= 0
+        results = (ids[0][keep].tolist(),)
+        if include_distances:
+            results += (d[0][keep].tolist(),)
+        if meta_db:
+            results += (self._metadata(results[0]),)
+        return results
+
+    # The reference's default mode asks Annoy for approximate neighbours
+    # (morna.py:632-678).  The forest is out of scope; exact search answers instead.
+    def search_nn(self, num_neighbors, search_k=None, include_distances=True, meta_db=False):
+        return self.exact_search_nn(num_neighbors, include_distances, meta_db)
+
+    def search_member_n(self, query_id, num_neighbors, search_k=None, include_distances=True,
+                        meta_db=False, out=None):
+        """morna.py:733-787 with the stored row as the query (float32 values), run
+        through the exact scan."""
+        import sys
+        out = out or sys.stdout
+        out.write("querying by sample id " + str(query_id) + "\n")
+        try:
+            internal_id = self.internal_id_map[query_id]
+        except KeyError:
+            raise ValueError("Querying sample id " + str(query_id) + " is not possible because no internal "
+                             "id is mapped to that sample id. Likely no sample with that id was included "
+                             "in the index.")
+        out.write("this is internal id " + str(internal_id) + "\n")
+        if not (self.row_lo <= internal_id < self.row_hi):
+            raise ValueError("internal id %d is not resident on this shard" % internal_id)
+        self.query_sample = self.vectors[internal_id - self.row_lo, :self.dim].to(torch.float64).cpu().tolist()
+        return self.exact_search_nn(num_neighbors, include_distances, meta_db)
+
+    def _metadata(self, internal_ids):
+        import sqlite3
+        conn = sqlite3.connect(self.basename + ".meta.mor")
+        cur = conn.cursor()
+        out = []
+        for iid in internal_ids:
+            cur.execute("SELECT keywords FROM metadata WHERE sample_id=?", (str(self.inverse_lookup(iid)),))
+            out.append(cur.fetchone())
+        conn.close()
+        return out

@@ -1,0 +1,320 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  GPU only."""
+import ctypes
+import hashlib
+import io
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import c_oracle
+from oracle import morna_oracle as mo
+from tests.helpers import GOLDEN, check_order_rule, check_topk, load_reference_vectors, tiny_lines
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from morna_b200 import _lib
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return _lib.load()
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------ K1 hashing
+def test_hash_kernel_bit_exact(lib):
+    from morna_b200 import _lib
+    rng = np.random.default_rng(3)
+    keys = ["", "a", "ab", "abc", "abcd", "abcde", "chr1 14830 14929", "chr1 14830 14969", "chr1 15039 15795"]
+    for _ in range(5000):
+        chrom = "chr" + str(rng.choice(list(range(1, 23)) + ["X", "Y"]))
+        start = int(rng.integers(1, 2.4e8))
+        keys.append("%s %d %d" % (chrom, start, start + int(rng.integers(50, 5e5))))
+    for dim in (3000, 500, 30000, 7, 1):
+        raw_o, bucket_o, sign_o = c_oracle.hash_rows(keys, dim)
+        blobs = [k.encode() for k in keys]
+        off = np.zeros(len(keys) + 1, np.int32)
+        off[1:] = np.cumsum([len(b) for b in blobs])
+        packed = np.frombuffer(b"".join(blobs) + b"\0", np.uint8).copy()
+        raw = torch.empty(len(keys), dtype=torch.int32, device="cuda")
+        bucket = torch.empty_like(raw)
+        sign = torch.empty(len(keys), dtype=torch.int8, device="cuda")
+        rc = lib.morna_hash_junctions(_lib.dev_ptr(dev(packed)), _lib.dev_ptr(dev(off)), len(keys), dim,
+                                      _lib.dev_ptr(raw), _lib.dev_ptr(bucket), _lib.dev_ptr(sign), _lib.stream_ptr())
+        assert rc == 0
+        assert np.array_equal(raw.cpu().numpy(), raw_o)
+        assert np.array_equal(bucket.cpu().numpy(), bucket_o)
+        assert np.array_equal(sign.cpu().numpy(), sign_o)
+    assert raw_o[6] == -28859081
+
+
+# ------------------------------------------------------------------ index build
+def build_both(lines, features, sample_count, threshold, store_skipped=True):
+    from morna_b200.index import MornaIndex
+    oracle = mo.go_index(lines, features=features, sample_count=sample_count, sample_threshold=threshold)
+    idx = MornaIndex(oracle.sample_count, "unused", dim=features, sample_threshold=threshold,
+                     store_skipped_rows=store_skipped)
+    idx.add_lines(lines)
+    idx.build(n_trees=20)
+    return oracle, idx
+
+
+@pytest.mark.parametrize("case_no", [0, 1, 2])
+def test_index_build_reference_unittest_inputs(case_no):
+    vec = load_reference_vectors()
+    case = vec["cases"][case_no]
+    lines = [l + "\n" for l in vec[case["input"]]]
+    for features in (case["features"], 40, 7):
+        oracle, idx = build_both(lines, features, case["sample_count"], case["sample_threshold"])
+        assert idx.get_n_items() == oracle.new_internal_id == case["n_items"]
+        assert idx.internal_id_map == oracle.internal_id_map
+        assert idx.skipped == oracle.skipped and idx.junc_id == oracle.junc_id
+        assert dict(idx.sample_frequencies) == dict(oracle.sample_frequencies)
+        assert np.array_equal(idx.accumulator_f64(), oracle.matrix_f64())     # bit-exact doubles
+        assert np.array_equal(idx.matrix_f32(), oracle.matrix_f32())
+
+
+def test_index_build_tiny_fixture_bit_exact():
+    with open(os.path.join(GOLDEN, "tiny_expected.json")) as fh:
+        exp = json.load(fh)
+    oracle, idx = build_both(tiny_lines(), 3000, None, 100)
+    assert idx.get_n_items() == exp["n_kept"] == 6850
+    assert idx.internal_id_map == oracle.internal_id_map
+    raw, bucket, sign = (t.cpu().numpy() for t in idx.row_hash)
+    for j, row in enumerate(exp["rows"]):
+        assert (int(raw[j]), int(bucket[j]), int(sign[j])) == (row["hash"], row["bucket"], row["sign"])
+    S = idx.matrix_f32()
+    assert hashlib.sha256(np.ascontiguousarray(S).tobytes()).hexdigest() == exp["matrix_f32_sha256"]
+    assert np.array_equal(idx.accumulator_f64(), oracle.matrix_f64())
+
+
+def synthetic_rows(rng, n_rows, n_samples, dup_keys=True, descending=False):
+    lines = []
+    for j in range(n_rows):
+        if dup_keys and j % 7 == 3 and j > 10:
+            key = lines[int(rng.integers(0, j))].split("\t")[:3]
+        else:
+            start = int(rng.integers(1, 5000))
+            key = ["chr%d" % rng.integers(1, 4), str(start), str(start + int(rng.integers(1, 300)))]
+        size = int(min(n_samples, max(1, rng.lognormal(3.0, 1.5))))
+        samples = np.sort(rng.choice(n_samples, size=size, replace=False) + 1)
+        if descending:
+            samples = samples[::-1]
+        covs = 1 + rng.geometric(0.5, size=size) * rng.integers(1, 40, size=size)
+        lines.append("\t".join(key + ["+", "GT", "AG", ",".join(map(str, samples)), ",".join(map(str, covs))]) + "\n")
+    return lines
+
+
+@pytest.mark.parametrize("features,threshold,n_samples", [(13, 3, 300), (500, 20, 2000), (3000, 1, 50), (64, 40, 30000)])
+def test_index_build_synthetic_bit_exact(features, threshold, n_samples):
+    rng = np.random.default_rng(features + threshold)
+    lines = synthetic_rows(rng, 400, n_samples, descending=(features == 500))
+    oracle, idx = build_both(lines, features, None, threshold)
+    assert idx.internal_id_map == oracle.internal_id_map
+    assert idx.get_n_items() == oracle.new_internal_id
+    assert np.array_equal(idx.accumulator_f64(), oracle.matrix_f64())
+    assert np.array_equal(idx.matrix_f32(), oracle.matrix_f32())
+    # pad columns of the device rows are zero
+    if idx.ld > idx.dim:
+        assert float(idx.vectors[:, idx.dim:].abs().max()) == 0.0
+
+
+def test_index_build_id_range_shards_concatenate():
+    from morna_b200.index import MornaIndex
+    rng = np.random.default_rng(21)
+    lines = synthetic_rows(rng, 300, 500)
+    oracle = mo.go_index(lines, features=100, sample_threshold=5)
+    parts = []
+    n = oracle.new_internal_id
+    for lo, hi in ((0, n // 3), (n // 3, n // 2), (n // 2, n)):
+        idx = MornaIndex(oracle.sample_count, "unused", dim=100, sample_threshold=5)
+        idx.add_lines(lines)
+        idx.build(id_range=(lo, hi))
+        assert idx.internal_id_map == oracle.internal_id_map
+        parts.append(idx.matrix_f32())
+    assert np.array_equal(np.concatenate(parts), oracle.matrix_f32())
+
+
+def test_index_build_no_passing_rows_raises():
+    from morna_b200.index import MornaIndex
+    idx = MornaIndex(10, "unused", dim=40, sample_threshold=50)
+    idx.add_junction("chr1 1 2", [1, 2, 3], [1, 1, 1])
+    with pytest.raises(ValueError):
+        idx.build()
+    idx = MornaIndex(10, "unused", dim=40, sample_threshold=50, store_skipped_rows=True)
+    idx.add_junction("chr1 1 2", [1, 2, 3], [1, 1, 1])
+    with pytest.raises(ValueError):
+        idx.build()
+
+
+# ------------------------------------------------------------------ exact search
+def make_search(S, **kw):
+    from morna_b200.search import MornaSearch
+    return MornaSearch(vectors=S, stats=(S.shape[0], S.shape[0], S.shape[1]), **kw)
+
+
+def test_distances_match_oracle_and_self_distance_is_zero(lib):
+    from morna_b200 import _lib
+    rng = np.random.default_rng(8)
+    for n, d in ((257, 3000), (100, 37), (33, 4), (1000, 130)):
+        S = rng.standard_normal((n, d)).astype(np.float32)
+        S[5] = 0.0
+        S[7] = S[3] * 2
+        srch = make_search(S)
+        Q = np.concatenate([S[:9].astype(np.float64), rng.standard_normal((4, d))])
+        Q[10] = 0.0
+        dq = dev(Q)
+        dist = torch.empty((Q.shape[0], n), dtype=torch.float64, device="cuda")
+        rc = lib.morna_angular_distances(_lib.dev_ptr(srch.vectors), _lib.dev_ptr(srch.pp), n, d, srch.ld,
+                                         _lib.dev_ptr(dq), Q.shape[0], d, _lib.dev_ptr(dist), n, _lib.stream_ptr())
+        assert rc == 0
+        got = dist.cpu().numpy()
+        for qi in range(Q.shape[0]):
+            want = c_oracle.distances(S, Q[qi])
+            np.testing.assert_allclose(got[qi], want, rtol=0, atol=2e-7 if qi in (3, 7) else 1e-12)
+        for i in range(9):
+            if i != 5:
+                assert got[i, i] == 0.0                      # stored row vs itself: exactly 0
+        assert np.all(got[5] == math.sqrt(2.0)) and np.all(got[10] == math.sqrt(2.0))   # zero norm -> sqrt(2)
+        assert np.all(got[:, 5] == math.sqrt(2.0))
+
+
+def run_select(lib, keys, ids, k, id_base=0):
+    from morna_b200 import _lib
+    nq, n = keys.shape
+    out_i = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+    out_d = torch.empty((nq, k), dtype=torch.float64, device="cuda")
+    ws = _lib.workspace(lib.morna_select_topk_workspace_bytes(n, nq, k), "cuda")
+    dk = dev(keys)
+    di = dev(ids) if ids is not None else None
+    rc = lib.morna_select_topk(_lib.dev_ptr(dk), _lib.dev_ptr(di) if di is not None else None, n, n, id_base, nq, k,
+                               _lib.dev_ptr(out_i), _lib.dev_ptr(out_d), _lib.dev_ptr(ws), ws.numel(),
+                               _lib.stream_ptr())
+    assert rc == 0
+    return out_i.cpu().numpy(), out_d.cpu().numpy()
+
+
+@pytest.mark.parametrize("n", [1, 5, 100, 1023, 1024, 1025, 8191, 8192, 8193, 21504, 100003])
+def test_select_topk_exact_order(lib, n):
+    rng = np.random.default_rng(n)
+    for k in (1, 20, 100, 1000, 2048):
+        nq = 3
+        keys = rng.random((nq, n))
+        keys[1] = np.round(keys[1] * 8) / 8            # heavy ties
+        keys[2, : n // 2] = 0.0                        # half of the rows tie at distance 0
+        ids_out, d_out = run_select(lib, keys, None, k, id_base=1000)
+        for q in range(nq):
+            want_i, want_d = mo.topk_rule(keys[q], k, ids=np.arange(n) + 1000)
+            m = len(want_i)
+            assert np.array_equal(ids_out[q, :m], want_i), (n, k, q)
+            assert np.array_equal(d_out[q, :m], want_d)
+            assert np.all(ids_out[q, m:] == -1) and np.all(np.isinf(d_out[q, m:]))
+
+
+def test_select_topk_explicit_ids_with_padding(lib):
+    rng = np.random.default_rng(4)
+    n, k = 800, 100                                   # e.g. 8 ranks x 100 gathered entries
+    keys = np.round(rng.random((2, n)) * 50) / 50
+    ids = rng.permutation(10 * n)[: 2 * n].reshape(2, n).astype(np.int32)
+    ids[0, 700:] = -1
+    keys[0, 700:] = np.inf
+    got_i, got_d = run_select(lib, keys, ids, k)
+    for q in range(2):
+        valid = ids[q] >= 0
+        want_i, want_d = mo.topk_rule(keys[q][valid], k, ids=ids[q][valid])
+        assert np.array_equal(got_i[q], want_i) and np.array_equal(got_d[q], want_d)
+
+
+def test_exact_search_matches_oracle_gaussian():
+    rng = np.random.default_rng(12)
+    n, d, k = 3000, 3000, 100
+    S = rng.standard_normal((n, d)).astype(np.float32)
+    srch = make_search(S)
+    qrows = rng.permutation(n)[:6]
+    Q = np.concatenate([S[qrows].astype(np.float64), S[qrows[:3]] + 0.05 * rng.standard_normal((3, d))])
+    ids, dist = srch.exact_search_batch(Q, k)
+    for qi in range(Q.shape[0]):
+        true_d = c_oracle.distances(S, Q[qi])
+        want_i, want_d = c_oracle.exact_search(S, Q[qi], k)
+        check_topk(true_d, ids[qi], dist[qi], tol=1e-9, dist_tol=1e-5)
+        check_order_rule(ids[qi], dist[qi])
+        assert np.array_equal(ids[qi], want_i)         # no near-ties in Gaussian data: identical ids
+        np.testing.assert_allclose(dist[qi], want_d, rtol=0, atol=1e-9)
+
+
+def test_exact_search_tiny_fixture_matches_golden():
+    with open(os.path.join(GOLDEN, "tiny_expected.json")) as fh:
+        exp = json.load(fh)
+    oracle = mo.go_index(tiny_lines(), features=3000, sample_threshold=100)
+    S = oracle.matrix_f32()
+    srch = make_search(S)
+    for q in exp["queries"]:
+        query = S[q["internal_id"]].astype(np.float64)
+        ids, dist = srch.exact_search_batch(query[None, :], 20)
+        true_d = c_oracle.distances(S, query)
+        check_topk(true_d, ids[0], dist[0], tol=1e-7, dist_tol=1e-5)
+        check_order_rule(ids[0], dist[0])
+    q0 = exp["queries"][0]       # rows with <= 2 non-zeros: sums are bit-equal, so ids are too
+    ids, dist = srch.exact_search_batch(S[q0["internal_id"]].astype(np.float64)[None, :], 20)
+    assert ids[0].tolist() == q0["ids"] and dist[0].tolist() == q0["dists"]
+
+
+def test_exact_search_k_larger_than_n_and_shards():
+    rng = np.random.default_rng(2)
+    S = rng.standard_normal((50, 40)).astype(np.float32)
+    srch = make_search(S)
+    ids, dist = srch.exact_search_batch(S[:2].astype(np.float64), 64)
+    assert np.all(ids[:, 50:] == -1) and np.all(np.isinf(dist[:, 50:]))
+    want_i, _ = c_oracle.exact_search(S, S[0].astype(np.float64), 64)
+    assert np.array_equal(ids[0, :50], want_i)
+    # two row shards + merge == one shard
+    from morna_b200 import dist as mdist
+    parts = [make_search(S, shard=(r, 2)) for r in range(2)]
+    q = torch.from_numpy(S[:5].astype(np.float64)).cuda()
+    lists = [p.exact_search_device(q, 10) for p in parts]
+    mi, md = mdist.merge_topk(torch.cat([l[0] for l in lists], 1), torch.cat([l[1] for l in lists], 1), 10)
+    full_i, full_d = srch.exact_search_device(q, 10)
+    assert torch.equal(mi, full_i) and torch.equal(md, full_d)
+
+
+# ------------------------------------------------------------------ CLI end to end (BASELINE config 1)
+def test_cli_index_then_exact_search_of_in_index_sample(tmp_path):
+    from morna_b200 import cli, files
+    with open(os.path.join(GOLDEN, "tiny_expected.json")) as fh:
+        exp = json.load(fh)
+    base = str(tmp_path / "tiny")
+    out = io.StringIO()
+    assert cli.main(["index", "--intropolis", os.path.join(GOLDEN, "tiny_intropolis.tsv"), "-x", base,
+                     "--features", "3000"], stdout=out) == 0
+    assert files.read_stats(base) == (6850, 6850, 3000)
+    assert files.read_freq(base)["chr1 14830 14929"] == 2040
+    assert files.read_map(base)[21504] == 6595
+    S = files.read_vectors(base)
+    assert hashlib.sha256(np.ascontiguousarray(S).tobytes()).hexdigest() == exp["matrix_f32_sha256"]
+    out = io.StringIO()
+    assert cli.main(["search", "-x", base, "-q", "12", "-e", "-d", "-r", "20"], stdout=out) == 0
+    lines = out.getvalue().splitlines()
+    assert lines[0] == "querying by sample id 12" and lines[1] == "this is internal id 0"
+    got = [l.split("\t") for l in lines[2:]]
+    assert [int(r[1]) for r in got] == exp["queries"][0]["ids"]
+    assert [r[2] for r in got] == ["0.0"] * 20 and got[0][0] == "1."
+    # out-of-index query from a raw junction list
+    out = io.StringIO()
+    query = "chr1\t14830\t14929\t3\nchr1\t14830\t14969\t5\nchr9\t1\t2\t100\n"
+    assert cli.main(["search", "-x", base, "-f", "raw", "-e", "-d", "-r", "5"], stdin=io.StringIO(query), stdout=out) == 0
+    freq = files.read_freq(base)
+    qvec = mo.finalize_query({("chr1", 14830, 14929): 3, ("chr1", 14830, 14969): 5}, freq, 6850, 3000)
+    want_i, want_d = c_oracle.exact_search(np.asarray(S), np.asarray(qvec), 5)
+    got = [l.split("\t") for l in out.getvalue().splitlines()]
+    true_d = c_oracle.distances(np.asarray(S), np.asarray(qvec))
+    check_topk(true_d, [int(r[1]) for r in got], [float(r[2]) for r in got], tol=1e-7, dist_tol=1e-5)
+    with pytest.raises(ValueError):
+        cli.main(["search", "-x", base, "-q", "999999", "-e"], stdout=io.StringIO())

@@ -1,0 +1,132 @@
+"""CPU-only checks: the C-ABI library loads and exports the header's symbols,
+file formats, parsers, CLI plumbing.  No compute calls (no GPU here)."""
+import ctypes
+import io
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+
+from morna_b200 import _lib, cli, files, parse
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "morna_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(morna_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(_lib.SO_PATH):
+        from morna_b200 import build
+        build.build()
+    lib = ctypes.CDLL(_lib.SO_PATH)
+    declared = header_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), name + " declared in include/morna_b200.h but not exported"
+    assert set(declared) == set(_lib.EXPORTED_SYMBOLS), "ctypes table and header disagree"
+    assert _lib.load().morna_abi_version() == 1
+    assert _lib.load().morna_status_string(-2) == b"workspace too small"
+
+
+def test_idf_host_matches_math_log():
+    import math
+    lib = _lib.load()
+    freq = np.array([2040, 6210, 1664, 5, 0], dtype=np.int64)
+    ok = np.array([1, 1, 1, 0, 1], dtype=np.uint8)
+    out = np.empty(5)
+    assert lib.morna_idf_host(freq.ctypes.data, ok.ctypes.data, 5, 6850, out.ctypes.data) == 0
+    assert out[:3].tolist() == [math.log(6850.0 / f) for f in (2040, 6210, 1664)]
+    assert out[3] == 0.0 and out[4] == 0.0
+
+
+def test_product_path_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from morna_b200.index import MornaIndex
+    with pytest.raises(_lib.MornaLibraryError):
+        MornaIndex(10, "x")
+    from morna_b200.search import MornaSearch
+    with pytest.raises(_lib.MornaLibraryError):
+        MornaSearch(vectors=np.zeros((1, 4), np.float32), stats=(1, 1, 4))
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, names in os.walk(os.path.join(ROOT, "morna_b200")):
+        for name in names:
+            if name.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, name)).read()
+                assert "oracle" not in text.replace("test oracle", ""), os.path.join(dirpath, name)
+
+
+def test_index_files_round_trip_and_py2_protocol(tmp_path):
+    base = str(tmp_path / "idx")
+    files.write_stats(base, 6850, 6850, 3000)
+    assert open(base + ".stats.mor").read() == "6850\n6850\n3000\n"
+    assert files.read_stats(base) == (6850, 6850, 3000)
+    files.write_freq(base, {"chr1 14830 14929": 2040})
+    raw = open(base + ".freq.mor", "rb").read()
+    assert raw[:2] == b"\x80\x02" and b"defaultdict" in raw          # protocol 2, defaultdict
+    freq = files.read_freq(base)
+    assert freq["chr1 14830 14929"] == 2040 and freq["absent"] == 0
+    files.write_map(base, {12: 0, np.int64(1): np.int32(2040)})
+    assert files.read_map(base) == {12: 0, 1: 2040}
+    m = np.random.default_rng(0).standard_normal((5, 7)).astype(np.float32)
+    files.write_vectors(base, m)
+    assert np.array_equal(files.read_vectors(base), m)
+    # a Python 2 style pickle (str keys as bytes) still loads
+    with open(base + ".map.mor", "wb") as fh:
+        fh.write(pickle.dumps({3: 1}, protocol=2))
+    assert files.read_map(base) == {3: 1}
+
+
+def test_annoy_item_rows(tmp_path):
+    import struct
+    m = np.arange(12, dtype=np.float32).reshape(3, 4)
+    blob = b"".join(struct.pack("<iii", 1, 0, 0) + m[i].tobytes() for i in range(3))
+    path = str(tmp_path / "a.annoy.mor")
+    open(path, "wb").write(blob + b"\0" * 28)
+    assert np.array_equal(files.read_annoy_item_vectors(path, 3, 4), m)
+
+
+def test_tokenizer_and_row_batch():
+    key, s, c = parse.tokenize_line("chr10\t101039923\t101040322\t-\tGC\tAG\t1,2,3,4\t1,1,1,5\n")
+    assert key == "chr10 101039923 101040322" and s == [1, 2, 3, 4] and c == [1, 1, 1, 5]
+    batch = parse.RowBatch()
+    batch.add(key, s, c)
+    batch.add("chrX 1 2", [7], [9])
+    packed, key_off, row_off, samples, covs = batch.finish()
+    assert bytes(packed[key_off[1]:key_off[2]]) == b"chrX 1 2"
+    assert row_off.tolist() == [0, 4, 5] and samples.tolist() == [1, 2, 3, 4, 7] and covs.tolist() == [1, 1, 1, 5, 9]
+    assert parse.count_samples(["a\tb\t1,2\t3\n", "a\tb\t2,03\t3\n"]) == 3   # strings, not ints
+
+
+def test_query_stream_parsers():
+    raw = list(parse.junctions_from_raw_stream(io.StringIO("chr1\t10\t20\t3\n")))
+    assert raw == [("chr1", 10, 20, 3)]
+    bed = "chr1\t100\t500\tx\t7\t+\t100\t500\t0\t3\t50,60,40,\t0,150,360,\n"
+    assert list(parse.junctions_from_bed_stream(io.StringIO(bed))) == [("chr1", 151, 250, 7), ("chr1", 311, 460, 7)]
+    sam = ("@HD\tVN:1.0\n"
+           "r1\t0\tchr2\t1000\t60\t10M100N5M2D3M50N7M\t*\t0\t0\tACGT\t*\n"
+           "r2\t4\tchr2\t1000\t60\t10M100N5M\t*\t0\t0\tACGT\t*\n"
+           "r3\t256\tchr2\t1000\t60\t10M100N5M\t*\t0\t0\tACGT\t*\n"
+           "r4\t0\tchr2\t1000\t60\t25M\t*\t0\t0\tACGT\t*\n")
+    assert list(parse.junctions_from_sam_stream(io.StringIO(sam))) == [("chr2", 1010, 1109, 1), ("chr2", 1120, 1169, 1)]
+
+
+def test_cli_parser_defaults_match_reference():
+    p = cli.build_parser()
+    a = p.parse_args(["index", "--intropolis", "x.gz"])
+    assert (a.basename, a.features, a.n_trees, a.sample_count, a.sample_threshold, a.buffer_size) == \
+        ("morna", 3000, 200, None, 100, 1024)
+    s = p.parse_args(["search", "-x", "idx", "-e", "-d", "-q", "12"])
+    assert (s.results, s.search_k, s.format, s.exact, s.distances, s.query_id) == (20, 100, "sam", True, True, 12)
+    out = io.StringIO()
+    cli.results_output(([3, 1], [0.0, 1.4142135623730951]), out)
+    assert out.getvalue() == "1.\t3\t0.0\n2.\t1\t1.41421356237\n"
