@@ -152,6 +152,40 @@ int morna_knn_exact(const float *vectors, const double *pp, int64_t n, int32_t d
                     int32_t *out_ids, double *out_dist,
                     void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------ batched search (tensor cores) */
+
+/* Leading dimension (in halves) of the fp16 tensor-core operand for `dim` features:
+ * dim rounded up to the 64-element K tile. */
+int64_t morna_tensor_operand_ld(int32_t dim);
+
+/* Build the tensor-core operand of an index block: hs[i] = fp16(v[i] / |v[i]|), zero padded
+ * to ld_h, and rho_max = max_i |v[i]/|v[i]| - hs[i]|_2, the rounding residual that bounds the
+ * fp16 score error.  Index-side, once per loaded block.
+ *   hs      [dev] fp16[n * ld_h]      rho_max [dev] float[1] */
+int morna_prepare_tensor_operand(const float *vectors, const double *pp, int64_t n, int32_t dim,
+                                 int64_t ld, void *hs, int64_t ld_h, float *rho_max, void *stream);
+
+/* exact_search_nn for a batch of queries (morna.py:681-712) with the N x D contraction on the
+ * tcgen05 tensor cores: fp16 scores with a rigorous error bound select a candidate superset
+ * of the true top-k, which is re-ranked with the same FP64 sums as morna_knn_exact, so ids
+ * and distances are identical to morna_knn_exact.  n <= 131072 rows per call.
+ *   overflow [dev] uint8[nq]  1 where a candidate list overflowed (massive ties): those
+ *                             queries hold id -1 / +inf and must be answered by morna_knn_exact
+ *   stats    [dev] int32[4]   {overflowed queries, sum of first-pass survivors,
+ *                              sum of re-ranked candidates, max re-ranked candidates} */
+size_t morna_knn_batched_workspace_bytes(int64_t n, int64_t nq, int32_t dim, int32_t k);
+int morna_knn_batched(const float *vectors, const double *pp, const void *hs, int64_t ld_h,
+                      const float *rho_max, int64_t n, int32_t dim, int64_t ld, int32_t id_base,
+                      const double *queries, int64_t nq, int64_t q_ld, int32_t k,
+                      int32_t *out_ids, double *out_dist, uint8_t *overflow, int32_t *stats,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* Test hook: raw fp16 tensor-core scores [nq x n] (n <= 8192) and the per-query bound eps. */
+int morna_debug_tensor_scores(const void *hs, int64_t ld_h, const float *rho_max, int64_t n, int32_t dim,
+                              const double *queries, int64_t nq, int64_t q_ld, float *scores,
+                              int64_t scores_ld, float *eps_out, void *workspace, size_t workspace_bytes,
+                              void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,672 @@
+// Batched exact angular kNN on the tensor cores.
+//
+//   1. rows and queries are normalised and rounded to fp16 (prep kernels); the rounding
+//      residual norms give a rigorous per-query bound eps on |fp16 score - true cosine|
+//   2. a TMA-fed tcgen05 GEMM (fp16 x fp16 -> fp32 in TMEM) scores queries x samples;
+//      its epilogue either dumps a pilot block of scores or keeps only the scores above a
+//      per-query threshold  thr = (k-th largest pilot score) - 2*eps
+//   3. per query, the exact k-th largest fp16 score a_k over the survivors is found and
+//      every sample with score >= a_k - 2*eps goes to the final candidate list -- a
+//      superset of the true top-k (ties included)
+//   4. candidates are re-ranked with the same FP64 sums the exact scan uses, and sorted
+//      under the reference order, so ids and distances equal morna_knn_exact bit for bit.
+// Replaces the N x D Python loop of exact_search_nn (morna.py:697-712) for query batches.
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace morna {
+
+// ------------------------------------------------------------------ operand preparation
+constexpr int kPrepThreads = 256;
+
+// warp per stored row: h = fp16(v / |v|), residual norm -> global max
+__global__ void __launch_bounds__(kPrepThreads)
+prep_samples_kernel(const float *__restrict__ vectors, const double *__restrict__ pp, int64_t n, int64_t ld,
+                    __half *__restrict__ hs, int64_t ld_h, float *__restrict__ rho_max) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * (kPrepThreads / 32);
+    const int chunks = (int)(ld >> 2), chunks_h = (int)(ld_h >> 2);
+    for (int64_t row = (int64_t)blockIdx.x * (kPrepThreads / 32) + (threadIdx.x >> 5); row < n; row += warps_total) {
+        const float4 *src = reinterpret_cast<const float4 *>(vectors + row * ld);
+        uint2 *dst = reinterpret_cast<uint2 *>(hs + row * ld_h);
+        const double norm = sqrt(pp[row]);
+        const double inv = norm > 0.0 ? 1.0 / norm : 0.0;
+        double res = 0.0;
+        for (int c = lane; c < chunks_h; c += 32) {
+            float4 v = c < chunks ? ldg_stream_f4(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            double x[4] = {v.x * inv, v.y * inv, v.z * inv, v.w * inv};
+            __half h[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                h[t] = __float2half_rn((float)x[t]);
+                double r = x[t] - (double)__half2float(h[t]);
+                res = fma(r, r, res);
+            }
+            uint2 packed;
+            packed.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+            packed.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+            dst[c] = packed;
+        }
+        res = warp_sum(res);
+        if (lane == 0) {
+            float rho = __double2float_ru(sqrt(res));
+            atomicMax(reinterpret_cast<int *>(rho_max), __float_as_int(rho));   // rho >= 0: int order == float order
+        }
+    }
+}
+
+// warp per query: qq with the canonical tree, fp16 normalised row, eps of the query
+__global__ void __launch_bounds__(kPrepThreads)
+prep_queries_kernel(const double *__restrict__ queries, int64_t nq, int64_t nq_pad, int32_t dim, int64_t q_ld,
+                    __half *__restrict__ hq, int64_t ld_h, double *__restrict__ qq_out, float *__restrict__ eps_out,
+                    const float *__restrict__ rho_max, float eps_acc) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * (kPrepThreads / 32);
+    const int chunks_h = (int)(ld_h >> 2);
+    for (int64_t row = (int64_t)blockIdx.x * (kPrepThreads / 32) + (threadIdx.x >> 5); row < nq_pad; row += warps_total) {
+        uint2 *dst = reinterpret_cast<uint2 *>(hq + row * ld_h);
+        if (row >= nq) {
+            for (int c = lane; c < chunks_h; c += 32) dst[c] = make_uint2(0u, 0u);
+            continue;
+        }
+        const double *q = queries + row * q_ld;
+        double acc = 0.0;
+        for (int c = lane; 4 * c < dim; c += 32) {       // same lane/chunk partition as the scan
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                double a = (4 * c + t < dim) ? q[4 * c + t] : 0.0;
+                acc = fma(a, a, acc);
+            }
+        }
+        acc = warp_sum(acc);
+        const double norm = sqrt(acc);
+        const double inv = norm > 0.0 ? 1.0 / norm : 0.0;
+        double res = 0.0;
+        for (int c = lane; c < chunks_h; c += 32) {
+            __half h[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                double x = (4 * c + t < dim) ? q[4 * c + t] * inv : 0.0;
+                h[t] = __float2half_rn((float)x);
+                double r = x - (double)__half2float(h[t]);
+                res = fma(r, r, res);
+            }
+            uint2 packed;
+            packed.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+            packed.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+            dst[c] = packed;
+        }
+        res = warp_sum(res);
+        if (lane == 0) {
+            qq_out[row] = acc;
+            const float rs = *rho_max, rq = __double2float_ru(sqrt(res));
+            // |fp16 score - cos| <= rho_s + |h_s| rho_q + accumulation error, |h_s| <= 1 + rho_s
+            eps_out[row] = __fadd_ru(__fadd_ru(rs, __fmul_ru(__fadd_ru(1.0f, rs), rq)), eps_acc);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ GEMM + filter epilogue
+namespace gemm {
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int THREADS = 192;                    // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int ACC_STAGES = 2, TMEM_COLS = ACC_STAGES * BN;   // 512 columns = all of TMEM
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+}  // namespace gemm
+
+struct GemmParams {
+    int32_t nq, n_begin, n_end, kblocks, m_blocks, n_tiles, mode, cap, id_base;
+    float *pilot; int64_t pilot_ld;
+    const float *thr; float *cand_score; int32_t *cand_id; int32_t *cand_cnt;
+};
+
+__global__ void __launch_bounds__(gemm::THREADS, 1)
+knn_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_s, GemmParams p) {
+    using namespace gemm;
+    using namespace tc;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B wants 1024-byte tiles
+    const uint32_t bars = base + STAGES * STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + ACC_STAGES + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 2 * ACC_STAGES);
+    volatile uint32_t *tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_q);
+        prefetch_tmap(&tmap_s);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<1>(tmem_slot, TMEM_COLS);
+        tmem_relinquish<1>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int total_tiles = p.m_blocks * p.n_tiles;
+    if (warp == 0) {
+        if (lane == 0) {     // ===== TMA producer
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int m_blk = t % p.m_blocks, n_tile = t / p.m_blocks;
+                const int row_q = m_blk * BM, row_s = p.n_begin + n_tile * BN;
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t a_dst = base + stage * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                    tma_load_2d(a_dst, &tmap_q, full_bar(stage), kb * BK, row_q);
+                    tma_load_2d(b_dst, &tmap_s, full_bar(stage), kb * BK, row_s);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {     // ===== MMA issuer (one thread)
+            constexpr uint32_t idesc = instr_desc_f16(BM, BN, /*fp16*/ 0);
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_src = base + stage * STAGE_BYTES, b_src = a_src + A_BYTES;
+                    const uint64_t da = smem_desc_sw128(a_src), db = smem_desc_sw128(b_src);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)      // +32 bytes along K = +2 in the address field
+                        umma_f16<1>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit(empty_bar(stage));             // frees the smem stage when the MMAs retire
+                    if (kb == p.kblocks - 1) umma_commit(tfull_bar(acc));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {                 // ===== epilogue: thread = TMEM lane = query row
+        const int quarter = warp & 3;                          // TMEM lanes a warp may read: 32*(warp%4)..+31
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int m_blk = t % p.m_blocks, n_tile = t / p.m_blocks;
+            const int row = m_blk * BM + quarter * 32 + lane;
+            const bool row_ok = row < p.nq;
+            const int col_tile = p.n_begin + n_tile * BN;
+            float thr = INFINITY;
+            if (p.mode == 1 && row_ok) thr = p.thr[row];
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + c * 32, r);
+                tmem_ld_wait();
+                const int col0 = col_tile + c * 32;
+                const int valid = min(32, p.n_end - col0);
+                if (p.mode == 0) {
+                    if (row_ok && valid > 0) {
+                        float *dst = p.pilot + (int64_t)row * p.pilot_ld + (col0 - p.n_begin);
+                        if (valid == 32) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4 *>(dst + j) =
+                                    make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < valid) dst[j] = __uint_as_float(r[j]);
+                        }
+                    }
+                } else {
+                    uint32_t mask = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        mask |= (uint32_t)(__uint_as_float(r[j]) >= thr && j < valid) << j;
+                    if (mask) {
+                        int at = atomicAdd(p.cand_cnt + row, __popc(mask));
+                        float *cs = p.cand_score + (int64_t)row * p.cap;
+                        int32_t *ci = p.cand_id + (int64_t)row * p.cap;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if ((mask >> j) & 1u) {
+                                if (at < p.cap) { cs[at] = __uint_as_float(r[j]); ci[at] = p.id_base + col0 + j; }
+                                ++at;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<1>(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ k-th largest + filter
+constexpr int kKthThreads = 256, kKthItems = 32, kKthMax = kKthThreads * kKthItems;   // 8192 entries
+
+__device__ __forceinline__ uint32_t float_key(float v) {      // monotone float -> uint
+    uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+struct KthParams {
+    int32_t k, n0, n_begin, id_base, cap, fcap;
+    const float *pilot; int64_t pilot_ld;
+    const float *eps;
+    float *thr;
+    float *cand_score; int32_t *cand_id; int32_t *cand_cnt;
+    int32_t *fin_id; int32_t *fin_cnt;
+    uint8_t *overflow; int32_t *stats;
+};
+
+// One CTA per query.  kPilot: input = the dumped pilot scores; output = thr and the pilot's
+// survivors appended to the candidate list.  !kPilot: input = candidate list; output = final list.
+template <bool kPilot>
+__global__ void __launch_bounds__(kKthThreads)
+kth_filter_kernel(KthParams p) {
+    __shared__ int s_warp[kKthThreads / 32];
+    __shared__ int s_total;
+    __shared__ int s_out;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    int count;
+    if (kPilot) count = p.n0;
+    else {
+        count = p.cand_cnt[q];
+        if (count > p.cap) {            // survivors were dropped: the exact scan must answer this query
+            if (tid == 0) { p.overflow[q] = 1; atomicAdd(p.stats + 0, 1); p.fin_cnt[q] = 0; }
+            return;
+        }
+    }
+    const int kk = min(p.k, count);
+    float score[kKthItems];
+    uint32_t key[kKthItems];
+#pragma unroll
+    for (int j = 0; j < kKthItems; ++j) {
+        int idx = j * kKthThreads + tid;
+        bool ok = idx < count;
+        float v = 0.f;
+        if (ok) v = kPilot ? p.pilot[(int64_t)q * p.pilot_ld + idx] : p.cand_score[(int64_t)q * p.cap + idx];
+        score[j] = v;
+        key[j] = ok ? float_key(v) : 0u;       // 0 sorts below every real score
+    }
+    // bitwise search for the key of the kk-th largest entry
+    uint32_t best = 0;
+    if (kk > 0) {
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t trial = best | (1u << bit);
+            int mine = 0;
+#pragma unroll
+            for (int j = 0; j < kKthItems; ++j) mine += key[j] >= trial;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(kFull, mine, o);
+            if ((tid & 31) == 0) s_warp[tid >> 5] = mine;
+            __syncthreads();
+            if (tid == 0) {
+                int tot = 0;
+#pragma unroll
+                for (int w = 0; w < kKthThreads / 32; ++w) tot += s_warp[w];
+                s_total = tot;
+            }
+            __syncthreads();
+            if (s_total >= kk) best = trial;
+        }
+    }
+    const float eps = p.eps[q];
+    // cannot prune while fewer than k scores have been seen
+    float cut = -INFINITY;
+    if (kk >= p.k) cut = __fsub_rd(key_float(best), __fmul_ru(2.0f, eps));
+    if (tid == 0) s_out = 0;
+    __syncthreads();
+    if (kPilot) {
+        if (tid == 0) p.thr[q] = cut;
+#pragma unroll
+        for (int j = 0; j < kKthItems; ++j) {
+            int idx = j * kKthThreads + tid;
+            if (idx < count && score[j] >= cut) {
+                int at = atomicAdd(&s_out, 1);
+                if (at < p.cap) {
+                    p.cand_score[(int64_t)q * p.cap + at] = score[j];
+                    p.cand_id[(int64_t)q * p.cap + at] = p.id_base + p.n_begin + idx;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) p.cand_cnt[q] = s_out;     // the filter pass appends after these
+    } else {
+#pragma unroll
+        for (int j = 0; j < kKthItems; ++j) {
+            int idx = j * kKthThreads + tid;
+            if (idx < count && score[j] >= cut) {
+                int at = atomicAdd(&s_out, 1);
+                if (at < p.fcap) p.fin_id[(int64_t)q * p.fcap + at] = p.cand_id[(int64_t)q * p.cap + idx];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int kept = s_out;
+            if (kept > p.fcap) { p.overflow[q] = 1; atomicAdd(p.stats + 0, 1); kept = 0; }
+            p.fin_cnt[q] = kept;
+            atomicAdd(p.stats + 1, count);
+            atomicAdd(p.stats + 2, kept);
+            atomicMax(p.stats + 3, kept);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ exact re-rank + final order
+constexpr int kRerankThreads = 256;
+
+// One CTA per query: FP64 distances of its candidates (canonical sums), then a bitonic sort
+// under the reference order and the first k written out.
+__global__ void __launch_bounds__(kRerankThreads)
+rerank_select_kernel(const float *__restrict__ vectors, const double *__restrict__ pp, int64_t ld, int32_t dim,
+                     int32_t id_base, const double *__restrict__ queries, int64_t q_ld,
+                     const double *__restrict__ qq, const int32_t *__restrict__ fin_id,
+                     const int32_t *__restrict__ fin_cnt, const uint8_t *__restrict__ overflow, int32_t fcap,
+                     int32_t k, int32_t *__restrict__ out_ids, double *__restrict__ out_dist) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *qs = reinterpret_cast<double *>(smem_raw);                 // [ld]
+    double *sd = qs + ld;                                              // [fcap]
+    int *si = reinterpret_cast<int *>(sd + fcap);                      // [fcap]
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int32_t *oi = out_ids + (int64_t)q * k;
+    double *od = out_dist + (int64_t)q * k;
+    if (overflow[q]) {                   // answered by the exact scan afterwards
+        for (int i = tid; i < k; i += kRerankThreads) { oi[i] = -1; od[i] = INFINITY; }
+        return;
+    }
+    const int count = min(fin_cnt[q], fcap);
+    for (int c = tid; c < ld; c += kRerankThreads) qs[c] = c < dim ? queries[(int64_t)q * q_ld + c] : 0.0;
+    int P = 32;
+    while (P < count) P <<= 1;
+    for (int i = tid; i < P; i += kRerankThreads) { sd[i] = INFINITY; si[i] = -1; }
+    __syncthreads();
+    const double qqv = qq[q];
+    const int chunks = (int)(ld >> 2);
+    for (int i = warp; i < count; i += kRerankThreads / 32) {
+        const int id = fin_id[(int64_t)q * fcap + i];
+        const int64_t row = id - id_base;
+        const float4 *src = reinterpret_cast<const float4 *>(vectors + row * ld);
+        double acc = 0.0;
+        for (int c = lane; c < chunks; c += 32) {
+            float4 v = __ldg(src + c);
+            double2 qa = *reinterpret_cast<const double2 *>(qs + 4 * c);
+            double2 qb = *reinterpret_cast<const double2 *>(qs + 4 * c + 2);
+            acc = fma((double)v.x, qa.x, acc); acc = fma((double)v.y, qa.y, acc);
+            acc = fma((double)v.z, qb.x, acc); acc = fma((double)v.w, qb.y, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) { sd[i] = angular_from_sums(pp[row], qqv, acc); si[i] = id; }
+    }
+    // bitonic sort of P entries under `before`
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = tid; i < (P >> 1); i += kRerankThreads) {
+                int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                bool asc = (lo & size) == 0;
+                double dl = sd[lo], dh = sd[hi];
+                int il = si[lo], ih = si[hi];
+                bool swap = asc ? before(dh, ih, dl, il) : before(dl, il, dh, ih);
+                if (swap) { sd[lo] = dh; sd[hi] = dl; si[lo] = ih; si[hi] = il; }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < k; i += kRerankThreads) {
+        bool ok = i < count && i < P && si[i] >= 0;
+        oi[i] = ok ? si[i] : -1;
+        od[i] = ok ? sd[i] : INFINITY;
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// fp16 row-major [rows x ld_h] -> tiles of box_rows x 64 halves, 128-byte swizzle, zero fill out of range
+static int make_tmap(CUtensorMap *map, const void *ptr, uint64_t rows, uint64_t ld_h, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return MORNA_ERR_CUDA;
+    cuuint64_t dims[2] = {ld_h, rows};
+    cuuint64_t strides[1] = {ld_h * sizeof(__half)};
+    cuuint32_t box[2] = {(cuuint32_t)gemm::BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return MORNA_ERR_CUDA; }
+    return MORNA_OK;
+}
+
+static int sm_count_b() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+constexpr int kCandCap = 4096, kFinCap = 1024, kPilotMax = kKthMax, kBatchedMaxRows = 131072;
+
+struct BatchWs {
+    size_t hq, qq, eps, pilot, thr, cand_score, cand_id, cand_cnt, fin_id, fin_cnt, total;
+    int64_t nq_pad, n0, pilot_ld;
+};
+static BatchWs batch_ws_layout(int64_t n, int64_t nq, int64_t ld_h) {
+    BatchWs w{};
+    w.nq_pad = (nq + gemm::BM - 1) / gemm::BM * gemm::BM;
+    w.n0 = n < kPilotMax ? n : kPilotMax;
+    w.pilot_ld = (w.n0 + 3) / 4 * 4;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t at = off; off += align_up(bytes, 256); return at; };
+    w.hq = take((size_t)w.nq_pad * ld_h * sizeof(__half));
+    w.qq = take((size_t)nq * sizeof(double));
+    w.eps = take((size_t)nq * sizeof(float));
+    w.pilot = take((size_t)nq * w.pilot_ld * sizeof(float));
+    w.thr = take((size_t)nq * sizeof(float));
+    w.cand_score = take((size_t)nq * kCandCap * sizeof(float));
+    w.cand_id = take((size_t)nq * kCandCap * sizeof(int32_t));
+    w.cand_cnt = take((size_t)nq * sizeof(int32_t));
+    w.fin_id = take((size_t)nq * kFinCap * sizeof(int32_t));
+    w.fin_cnt = take((size_t)nq * sizeof(int32_t));
+    w.total = off + 1024;
+    return w;
+}
+
+}  // namespace morna
+
+using namespace morna;
+
+extern "C" int64_t morna_tensor_operand_ld(int32_t dim) { return ((int64_t)dim + gemm::BK - 1) / gemm::BK * gemm::BK; }
+
+extern "C" int morna_prepare_tensor_operand(const float *vectors, const double *pp, int64_t n, int32_t dim,
+                                            int64_t ld, void *hs, int64_t ld_h, float *rho_max, void *stream) {
+    if (!vectors || !pp || !hs || !rho_max || n < 0 || dim <= 0 || ld < dim || (ld & 3) ||
+        ld_h != morna_tensor_operand_ld(dim))
+        return MORNA_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = (cudaStream_t)stream;
+    MORNA_CUDA_TRY(cudaMemsetAsync(rho_max, 0, sizeof(float), s));
+    if (n == 0) return MORNA_OK;
+    int64_t blocks = (n + 7) / 8;
+    if (blocks > (int64_t)sm_count_b() * 8) blocks = (int64_t)sm_count_b() * 8;
+    prep_samples_kernel<<<(unsigned)blocks, kPrepThreads, 0, s>>>(vectors, pp, n, ld, (__half *)hs, ld_h, rho_max);
+    MORNA_LAUNCH_CHECK();
+    return MORNA_OK;
+}
+
+extern "C" size_t morna_knn_batched_workspace_bytes(int64_t n, int64_t nq, int32_t dim, int32_t k) {
+    (void)k;
+    if (n <= 0 || nq <= 0 || dim <= 0) return 1024;
+    return batch_ws_layout(n, nq, morna_tensor_operand_ld(dim)).total;
+}
+
+extern "C" int morna_knn_batched(const float *vectors, const double *pp, const void *hs, int64_t ld_h,
+                                 const float *rho_max, int64_t n, int32_t dim, int64_t ld, int32_t id_base,
+                                 const double *queries, int64_t nq, int64_t q_ld, int32_t k, int32_t *out_ids,
+                                 double *out_dist, uint8_t *overflow, int32_t *stats, void *workspace,
+                                 size_t workspace_bytes, void *stream) {
+    if (!vectors || !pp || !hs || !rho_max || !queries || !out_ids || !out_dist || !overflow || !stats ||
+        n <= 0 || n > kBatchedMaxRows || nq <= 0 || dim <= 0 || ld < dim || (ld & 3) || q_ld < dim || k <= 0 ||
+        k > kFinCap / 2 || ld_h != morna_tensor_operand_ld(dim))
+        return MORNA_ERR_INVALID_ARGUMENT;
+    BatchWs w = batch_ws_layout(n, nq, ld_h);
+    if (!workspace || workspace_bytes < w.total) return MORNA_ERR_WORKSPACE_TOO_SMALL;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned char *ws = (unsigned char *)workspace;
+    __half *hq = (__half *)(ws + w.hq);
+    double *qq = (double *)(ws + w.qq);
+    float *eps = (float *)(ws + w.eps);
+    float *pilot = (float *)(ws + w.pilot);
+    float *thr = (float *)(ws + w.thr);
+    float *cand_score = (float *)(ws + w.cand_score);
+    int32_t *cand_id = (int32_t *)(ws + w.cand_id);
+    int32_t *cand_cnt = (int32_t *)(ws + w.cand_cnt);
+    int32_t *fin_id = (int32_t *)(ws + w.fin_id);
+    int32_t *fin_cnt = (int32_t *)(ws + w.fin_cnt);
+
+    MORNA_CUDA_TRY(cudaMemsetAsync(overflow, 0, (size_t)nq, s));
+    MORNA_CUDA_TRY(cudaMemsetAsync(stats, 0, 4 * sizeof(int32_t), s));
+    MORNA_CUDA_TRY(cudaMemsetAsync(cand_cnt, 0, (size_t)nq * sizeof(int32_t), s));
+
+    // fp32 accumulation of dim products, each add off by at most one truncation ulp of a
+    // partial sum bounded by |h_s||h_q| <= ~1; chain length dim/16 MMAs plus the in-MMA tree
+    const float eps_acc = (float)((double)(dim / 16 + 8) * 2.384185791015625e-07 * 1.01);
+    {
+        int64_t blocks = (w.nq_pad + 7) / 8;
+        if (blocks > (int64_t)sm_count_b() * 8) blocks = (int64_t)sm_count_b() * 8;
+        prep_queries_kernel<<<(unsigned)blocks, kPrepThreads, 0, s>>>(queries, nq, w.nq_pad, dim, q_ld, hq, ld_h, qq,
+                                                                    eps, rho_max, eps_acc);
+        MORNA_LAUNCH_CHECK();
+    }
+
+    CUtensorMap tmap_q, tmap_s;
+    int rc = make_tmap(&tmap_q, hq, (uint64_t)w.nq_pad, (uint64_t)ld_h, gemm::BM);
+    if (rc != MORNA_OK) return rc;
+    rc = make_tmap(&tmap_s, hs, (uint64_t)n, (uint64_t)ld_h, gemm::BN);
+    if (rc != MORNA_OK) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MORNA_CUDA_TRY(cudaFuncSetAttribute(knn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            gemm::SMEM_BYTES));
+        attr_set = true;
+    }
+    GemmParams gp{};
+    gp.nq = (int32_t)nq; gp.kblocks = (int32_t)(ld_h / gemm::BK); gp.m_blocks = (int32_t)(w.nq_pad / gemm::BM);
+    gp.cap = kCandCap; gp.id_base = id_base; gp.pilot = pilot; gp.pilot_ld = w.pilot_ld; gp.thr = thr;
+    gp.cand_score = cand_score; gp.cand_id = cand_id; gp.cand_cnt = cand_cnt;
+    auto launch_gemm = [&](int32_t n_begin, int32_t n_end, int32_t mode) -> int {
+        gp.n_begin = n_begin; gp.n_end = n_end; gp.mode = mode;
+        gp.n_tiles = (n_end - n_begin + gemm::BN - 1) / gemm::BN;
+        int tiles = gp.m_blocks * gp.n_tiles;
+        int grid = tiles < sm_count_b() ? tiles : sm_count_b();
+        knn_gemm_kernel<<<grid, gemm::THREADS, gemm::SMEM_BYTES, s>>>(tmap_q, tmap_s, gp);
+        MORNA_LAUNCH_CHECK();
+        return MORNA_OK;
+    };
+
+    KthParams kp{};
+    kp.k = k; kp.n0 = (int32_t)w.n0; kp.n_begin = 0; kp.id_base = id_base; kp.cap = kCandCap; kp.fcap = kFinCap;
+    kp.pilot = pilot; kp.pilot_ld = w.pilot_ld; kp.eps = eps; kp.thr = thr; kp.cand_score = cand_score;
+    kp.cand_id = cand_id; kp.cand_cnt = cand_cnt; kp.fin_id = fin_id; kp.fin_cnt = fin_cnt; kp.overflow = overflow;
+    kp.stats = stats;
+
+    rc = launch_gemm(0, (int32_t)w.n0, 0);                       // pilot block: dump scores
+    if (rc != MORNA_OK) return rc;
+    kth_filter_kernel<true><<<(unsigned)nq, kKthThreads, 0, s>>>(kp);
+    MORNA_LAUNCH_CHECK();
+    if (w.n0 < n) {
+        rc = launch_gemm((int32_t)w.n0, (int32_t)n, 1);          // the rest: keep scores above thr
+        if (rc != MORNA_OK) return rc;
+    }
+    kth_filter_kernel<false><<<(unsigned)nq, kKthThreads, 0, s>>>(kp);
+    MORNA_LAUNCH_CHECK();
+    const size_t rr_smem = (size_t)ld * sizeof(double) + (size_t)kFinCap * (sizeof(double) + sizeof(int));
+    if (rr_smem > 200 * 1024) return MORNA_ERR_INVALID_ARGUMENT;
+    if (rr_smem > 48 * 1024)
+        MORNA_CUDA_TRY(cudaFuncSetAttribute(rerank_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)rr_smem));
+    rerank_select_kernel<<<(unsigned)nq, kRerankThreads, rr_smem, s>>>(vectors, pp, ld, dim, id_base, queries, q_ld, qq,
+                                                                      fin_id, fin_cnt, overflow, kFinCap, k, out_ids,
+                                                                      out_dist);
+    MORNA_LAUNCH_CHECK();
+    return MORNA_OK;
+}
+
+// Raw fp16 tensor-core scores of a query block against the first n0 samples, plus the
+// per-query error bound -- used by tests to validate eps against exact cosines.
+extern "C" int morna_debug_tensor_scores(const void *hs, int64_t ld_h, const float *rho_max, int64_t n, int32_t dim,
+                                         const double *queries, int64_t nq, int64_t q_ld, float *scores,
+                                         int64_t scores_ld, float *eps_out, void *workspace, size_t workspace_bytes,
+                                         void *stream) {
+    if (!hs || !rho_max || !queries || !scores || !eps_out || n <= 0 || nq <= 0 || scores_ld < n || (scores_ld & 3) ||
+        ld_h != morna_tensor_operand_ld(dim))
+        return MORNA_ERR_INVALID_ARGUMENT;
+    BatchWs w = batch_ws_layout(n, nq, ld_h);
+    if (!workspace || workspace_bytes < w.total) return MORNA_ERR_WORKSPACE_TOO_SMALL;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned char *ws = (unsigned char *)workspace;
+    __half *hq = (__half *)(ws + w.hq);
+    double *qq = (double *)(ws + w.qq);
+    const float eps_acc = (float)((double)(dim / 16 + 8) * 2.384185791015625e-07 * 1.01);
+    int64_t blocks = (w.nq_pad + 7) / 8;
+    prep_queries_kernel<<<(unsigned)blocks, kPrepThreads, 0, s>>>(queries, nq, w.nq_pad, dim, q_ld, hq, ld_h, qq,
+                                                                eps_out, rho_max, eps_acc);
+    MORNA_LAUNCH_CHECK();
+    CUtensorMap tmap_q, tmap_s;
+    int rc = make_tmap(&tmap_q, hq, (uint64_t)w.nq_pad, (uint64_t)ld_h, gemm::BM);
+    if (rc != MORNA_OK) return rc;
+    rc = make_tmap(&tmap_s, hs, (uint64_t)n, (uint64_t)ld_h, gemm::BN);
+    if (rc != MORNA_OK) return rc;
+    MORNA_CUDA_TRY(cudaFuncSetAttribute(knn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
+    GemmParams gp{};
+    gp.nq = (int32_t)nq; gp.kblocks = (int32_t)(ld_h / gemm::BK); gp.m_blocks = (int32_t)(w.nq_pad / gemm::BM);
+    gp.n_begin = 0; gp.n_end = (int32_t)n; gp.mode = 0; gp.pilot = scores; gp.pilot_ld = scores_ld;
+    gp.n_tiles = (gp.n_end + gemm::BN - 1) / gemm::BN;
+    int tiles = gp.m_blocks * gp.n_tiles;
+    int grid = tiles < sm_count_b() ? tiles : sm_count_b();
+    knn_gemm_kernel<<<grid, gemm::THREADS, gemm::SMEM_BYTES, s>>>(tmap_q, tmap_s, gp);
+    MORNA_LAUNCH_CHECK();
+    return MORNA_OK;
+}

@@ -61,7 +61,7 @@ class MornaSearch(object):
             if isinstance(host, torch.Tensor):
                 block = host[self.row_lo:self.row_hi].to(torch.float32)
             else:
-                block = torch.from_numpy(np.ascontiguousarray(host[self.row_lo:self.row_hi], dtype=np.float32))
+                block = torch.from_numpy(np.array(host[self.row_lo:self.row_hi], dtype=np.float32, order="C"))
             self.vectors[:, :self.dim].copy_(block, non_blocking=False)
         self.pp = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
@@ -125,8 +125,11 @@ class MornaSearch(object):
         """queries: CUDA float64 [nq x dim] (row stride = queries.stride(0)).  Returns
         device (ids int32 [nq x k], dists float64 [nq x k]); ids are global internal
         ids (row_lo + local row); short lists are padded with id -1 / +inf."""
-        assert queries.is_cuda and queries.dtype == torch.float64 and queries.stride(1) == 1
+        assert queries.is_cuda and queries.dtype == torch.float64 and queries.dim() == 2
+        queries = queries.contiguous()
         nq = queries.shape[0]
+        q_ld = queries.shape[1]            # (a size-1 leading dimension may report stride 0)
+        assert q_ld == self.dim, "queries must be [nq x dim]"
         n = self.row_hi - self.row_lo
         dev = self.device
         out_ids = torch.full((nq, k), -1, dtype=torch.int32, device=dev)
@@ -137,9 +140,77 @@ class MornaSearch(object):
             ws = self._workspace(self.lib.morna_knn_exact_workspace_bytes(n, nq, k))
             _lib.check(self.lib.morna_knn_exact(
                 _lib.dev_ptr(self.vectors), _lib.dev_ptr(self.pp), n, self.dim, self.ld, self.row_lo,
-                _lib.ptr(queries), nq, queries.stride(0), k, _lib.dev_ptr(out_ids), _lib.dev_ptr(out_d),
+                _lib.ptr(queries), nq, q_ld, k, _lib.dev_ptr(out_ids), _lib.dev_ptr(out_d),
                 _lib.dev_ptr(ws), ws.numel(), _lib.stream_ptr(stream)), "morna_knn_exact")
         return out_ids, out_d
+
+    # ------------------------------------------------------------------ batched search (tensor cores)
+    BATCH_BLOCK_ROWS = 131072        # rows per morna_knn_batched call
+
+    def enable_tensor_path(self):
+        """Builds the fp16 tensor-core operand of the resident rows (once)."""
+        if getattr(self, "hs", None) is not None:
+            return
+        n, dev = self.row_hi - self.row_lo, self.device
+        self.ld_h = int(self.lib.morna_tensor_operand_ld(self.dim))
+        self.hs = torch.empty((max(n, 1), self.ld_h), dtype=torch.float16, device=dev)
+        self.rho_max = torch.zeros(1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.morna_prepare_tensor_operand(
+                _lib.dev_ptr(self.vectors), _lib.dev_ptr(self.pp), n, self.dim, self.ld, _lib.dev_ptr(self.hs),
+                self.ld_h, _lib.dev_ptr(self.rho_max), _lib.stream_ptr()), "morna_prepare_tensor_operand")
+        self._bws = None
+        self.last_stats = None
+
+    def batched_search_device(self, queries, k, stream=None, check_overflow=True):
+        """Same contract and same results as exact_search_device, with the N x D
+        contraction on the tensor cores (fp16 first pass with a rigorous error bound,
+        FP64 re-rank).  Queries whose candidate lists overflow (massive ties) are
+        answered by the exact scan."""
+        from . import dist as mdist
+        self.enable_tensor_path()
+        assert queries.is_cuda and queries.dtype == torch.float64 and queries.dim() == 2
+        queries = queries.contiguous()
+        nq, dev = queries.shape[0], self.device
+        n = self.row_hi - self.row_lo
+        assert queries.shape[1] == self.dim
+        if n == 0 or nq == 0 or k > 512:
+            return self.exact_search_device(queries, k, stream)
+        parts = []
+        stats_total = torch.zeros(4, dtype=torch.int64)
+        with torch.cuda.device(dev):
+            for b0 in range(0, n, self.BATCH_BLOCK_ROWS):
+                b1 = min(n, b0 + self.BATCH_BLOCK_ROWS)
+                out_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+                out_d = torch.empty((nq, k), dtype=torch.float64, device=dev)
+                overflow = torch.empty(nq, dtype=torch.uint8, device=dev)
+                stats = torch.empty(4, dtype=torch.int32, device=dev)
+                need = self.lib.morna_knn_batched_workspace_bytes(b1 - b0, nq, self.dim, k)
+                if self._bws is None or self._bws.numel() < need:
+                    self._bws = _lib.workspace(need, dev)
+                _lib.check(self.lib.morna_knn_batched(
+                    _lib.dev_ptr(self.vectors[b0:b1]), _lib.dev_ptr(self.pp[b0:b1]), _lib.dev_ptr(self.hs[b0:b1]),
+                    self.ld_h, _lib.dev_ptr(self.rho_max), b1 - b0, self.dim, self.ld, self.row_lo + b0,
+                    _lib.ptr(queries), nq, self.dim, k, _lib.dev_ptr(out_ids), _lib.dev_ptr(out_d),
+                    _lib.dev_ptr(overflow), _lib.dev_ptr(stats), _lib.dev_ptr(self._bws), self._bws.numel(),
+                    _lib.stream_ptr(stream)), "morna_knn_batched")
+                if check_overflow:
+                    st = stats.cpu()
+                    stats_total += st.to(torch.int64)
+                    if int(st[0]) > 0:                 # rare: ties wider than the candidate lists
+                        idx = overflow.nonzero().flatten()
+                        sub = MornaSearch.__new__(MornaSearch)
+                        sub.__dict__.update(self.__dict__)
+                        sub.vectors, sub.pp = self.vectors[b0:b1], self.pp[b0:b1]
+                        sub.row_lo, sub.row_hi, sub._ws = self.row_lo + b0, self.row_lo + b1, None
+                        e_ids, e_d = sub.exact_search_device(queries[idx], k, stream)
+                        out_ids[idx] = e_ids
+                        out_d[idx] = e_d
+                parts.append((out_ids, out_d))
+        self.last_stats = stats_total.tolist()
+        if len(parts) == 1:
+            return parts[0]
+        return mdist.merge_topk(torch.cat([p[0] for p in parts], 1), torch.cat([p[1] for p in parts], 1), k, stream)
 
     def exact_search_batch(self, queries, k):
         """Host entry: queries numpy [nq x dim] (float32 or float64) -> numpy (ids, dists)."""

@@ -1,0 +1,122 @@
+"""Tensor-core batched search: fp16 score error bound, and bit-identical results vs the exact scan."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import c_oracle
+from oracle import morna_oracle as mo
+from tests.helpers import GOLDEN, check_topk, tiny_lines
+
+pytestmark = pytest.mark.gpu
+
+
+def make_search(S, **kw):
+    from morna_b200.search import MornaSearch
+    return MornaSearch(vectors=S, stats=(S.shape[0], S.shape[0], S.shape[1]), **kw)
+
+
+def sparse_rows(rng, n, d, nnz):
+    S = np.zeros((n, d), np.float32)
+    for i in range(n):
+        cols = rng.choice(d, size=int(rng.integers(1, nnz + 1)), replace=False)
+        S[i, cols] = (rng.integers(1, 50, size=len(cols)) * rng.choice([-1.0, 1.0], size=len(cols))
+                      * rng.choice([0.098, 1.21, 1.415, 0.5], size=len(cols)))
+    return S
+
+
+@pytest.mark.parametrize("n,d,kind", [(2048, 3000, "gauss"), (1000, 37, "gauss"), (777, 130, "gauss"),
+                                      (3000, 3000, "sparse"), (512, 64, "sparse")])
+def test_fp16_scores_stay_within_the_rigorous_bound(n, d, kind):
+    from morna_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(n + d)
+    S = rng.standard_normal((n, d)).astype(np.float32) if kind == "gauss" else sparse_rows(rng, n, d, 3)
+    if kind == "gauss":
+        S *= np.exp(rng.standard_normal((n, 1))).astype(np.float32)      # mixed row scales
+    S[3] = 0.0
+    srch = make_search(S)
+    srch.enable_tensor_path()
+    Q = np.concatenate([S[:100].astype(np.float64), S[100:150] + 0.05 * rng.standard_normal((50, d)),
+                        rng.standard_normal((27, d))])
+    Q[120] = 0.0
+    nq = Q.shape[0]
+    dq = torch.from_numpy(Q).cuda()
+    ld_s = (n + 3) // 4 * 4
+    scores = torch.zeros((nq, ld_s), dtype=torch.float32, device="cuda")
+    eps = torch.zeros(nq, dtype=torch.float32, device="cuda")
+    ws = _lib.workspace(lib.morna_knn_batched_workspace_bytes(n, nq, d, 10), "cuda")
+    rc = lib.morna_debug_tensor_scores(_lib.dev_ptr(srch.hs), srch.ld_h, _lib.dev_ptr(srch.rho_max), n, d,
+                                       _lib.dev_ptr(dq), nq, d, _lib.dev_ptr(scores), ld_s, _lib.dev_ptr(eps),
+                                       _lib.dev_ptr(ws), ws.numel(), _lib.stream_ptr())
+    assert rc == 0
+    torch.cuda.synchronize()
+    got = scores.cpu().numpy()[:, :n].astype(np.float64)
+    S64 = S.astype(np.float64)
+    sn = np.linalg.norm(S64, axis=1)
+    qn = np.linalg.norm(Q, axis=1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cos = (Q @ S64.T) / (qn[:, None] * sn[None, :])
+    cos[~np.isfinite(cos)] = 0.0                       # zero-norm row or query: cosine defined as 0
+    err = np.abs(got - cos)
+    e = eps.cpu().numpy().astype(np.float64)
+    assert np.all(err <= e[:, None]), "fp16 score error %g exceeds bound %g" % (err.max(), e.min())
+    assert e.max() < 2e-3
+    assert err.max() > 0          # it really is a reduced-precision pass
+    print("max err %.3g, bound %.3g..%.3g" % (err.max(), e.min(), e.max()))
+
+
+@pytest.mark.parametrize("n,d,nq,k", [(3000, 3000, 300, 100), (20000, 512, 130, 20), (9000, 64, 257, 50),
+                                      (500, 3000, 5, 100), (8192, 256, 128, 10), (8449, 100, 129, 1)])
+def test_batched_equals_exact_scan_bit_for_bit(n, d, nq, k):
+    rng = np.random.default_rng(n * 7 + d)
+    S = rng.standard_normal((n, d)).astype(np.float32)
+    S[n // 2] = 0.0
+    srch = make_search(S)
+    rows = rng.permutation(n)[:nq]
+    Q = S[rows].astype(np.float64)
+    Q[1::3] += 0.05 * rng.standard_normal((len(Q[1::3]), d))
+    Q[2::7] = rng.standard_normal((len(Q[2::7]), d))
+    if nq > 4:
+        Q[4] = 0.0
+    q = torch.from_numpy(Q).cuda()
+    e_ids, e_d = srch.exact_search_device(q, k)
+    b_ids, b_d = srch.batched_search_device(q, k)
+    torch.cuda.synchronize()
+    # only the all-zero query (every row ties at sqrt(2)) may overflow into the exact scan
+    assert srch.last_stats[0] <= (1 if nq > 4 else 0), "unexpected overflow on gaussian data: %r" % (srch.last_stats,)
+    assert torch.equal(b_ids, e_ids)
+    assert torch.equal(b_d, e_d)
+    # and the exact scan is itself checked against the oracle for one query
+    true_d = c_oracle.distances(S, Q[0])
+    check_topk(true_d, b_ids[0].cpu().numpy()[: min(k, n)], b_d[0].cpu().numpy()[: min(k, n)], tol=1e-9)
+    print("stats", srch.last_stats, "per query survivors %.1f final %.1f" % (srch.last_stats[1] / nq, srch.last_stats[2] / nq))
+
+
+def test_batched_with_massive_ties_falls_back_to_exact_scan():
+    oracle = mo.go_index(tiny_lines(), features=3000, sample_threshold=100)
+    S = oracle.matrix_f32()
+    srch = make_search(S)
+    rows = np.array([0, 2040, 6595, 5, 4000, 17])
+    q = torch.from_numpy(S[rows].astype(np.float64)).cuda()
+    e_ids, e_d = srch.exact_search_device(q, 20)
+    b_ids, b_d = srch.batched_search_device(q, 20)
+    assert srch.last_stats[0] > 0            # thousands of rows tie at distance 0: lists overflow
+    assert torch.equal(b_ids, e_ids) and torch.equal(b_d, e_d)
+    with open(os.path.join(GOLDEN, "tiny_expected.json")) as fh:
+        exp = json.load(fh)
+    assert b_ids[0].tolist() == exp["queries"][0]["ids"]
+
+
+def test_batched_row_blocks_merge():
+    rng = np.random.default_rng(5)
+    S = rng.standard_normal((2600, 96)).astype(np.float32)
+    srch = make_search(S)
+    srch.BATCH_BLOCK_ROWS = 1024          # force three row blocks + merge
+    q = torch.from_numpy(S[:40].astype(np.float64)).cuda()
+    e_ids, e_d = srch.exact_search_device(q, 30)
+    b_ids, b_d = srch.batched_search_device(q, 30)
+    assert torch.equal(b_ids, e_ids) and torch.equal(b_d, e_d)

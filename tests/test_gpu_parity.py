@@ -47,7 +47,8 @@ def test_hash_kernel_bit_exact(lib):
         raw = torch.empty(len(keys), dtype=torch.int32, device="cuda")
         bucket = torch.empty_like(raw)
         sign = torch.empty(len(keys), dtype=torch.int8, device="cuda")
-        rc = lib.morna_hash_junctions(_lib.dev_ptr(dev(packed)), _lib.dev_ptr(dev(off)), len(keys), dim,
+        d_packed, d_off = dev(packed), dev(off)       # keep the inputs alive across the launch
+        rc = lib.morna_hash_junctions(_lib.dev_ptr(d_packed), _lib.dev_ptr(d_off), len(keys), dim,
                                       _lib.dev_ptr(raw), _lib.dev_ptr(bucket), _lib.dev_ptr(sign), _lib.stream_ptr())
         assert rc == 0
         assert np.array_equal(raw.cpu().numpy(), raw_o)
