@@ -168,8 +168,10 @@ def main():
     host_ids = torch.empty((nq, K), dtype=torch.int32).pin_memory()
     host_d = torch.empty((nq, K), dtype=torch.float64).pin_memory()
 
+    srch.enable_tensor_path()
+
     def step_resident():
-        ids, d = srch.exact_search_device(queries64, K)
+        ids, d = srch.batched_search_device(queries64, K)
         if args.rows_sharded and world > 1:
             ids, d = mdist.all_gather_topk(ids, d)
             ids, d = mdist.merge_topk(ids, d, K)
@@ -177,7 +179,7 @@ def main():
 
     def step_e2e():
         q = host_q.to(device, non_blocking=True)
-        ids, d = srch.exact_search_device(q, K)
+        ids, d = srch.batched_search_device(q, K)
         if args.rows_sharded and world > 1:
             ids, d = mdist.all_gather_topk(ids, d)
             ids, d = mdist.merge_topk(ids, d, K)
@@ -262,31 +264,36 @@ def main():
 
 
 def dominant_kernel_roofline(torch, lib, _lib, srch, queries64, peaks):
-    """Times the dominant kernel of the step by itself (CUDA events on the launching
-    stream).  Until the tcgen05 contraction lands this is the FP64 distance scan."""
-    nq = min(queries64.shape[0], 512)
-    n = srch.row_hi - srch.row_lo
-    dist = torch.empty((nq, n), dtype=torch.float64, device=srch.device)
-    call = lambda: _lib.check(lib.morna_angular_distances(
-        _lib.dev_ptr(srch.vectors), _lib.dev_ptr(srch.pp), n, srch.dim, srch.ld, _lib.dev_ptr(queries64), nq,
-        queries64.stride(0), _lib.dev_ptr(dist), n, _lib.stream_ptr()), "morna_angular_distances")
-    for _ in range(3):
-        call()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
-    e0.record()
-    for _ in range(reps):
-        call()
-    e1.record()
+    """Times the kernels of one step with CUDA events recorded on the launching stream at the
+    phase boundaries of morna_knn_batched; the dominant one is the tcgen05 GEMM's filter pass."""
+    from morna_b200.search import PHASE_NAMES, make_phase_events
+    events, arr = make_phase_events()
+    reps, acc = 5, [0.0] * 6
+    for _ in range(2):
+        srch.batched_search_device(queries64, K, phase_events=arr)
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    flops = 2.0 * nq * n * srch.dim
+    for _ in range(reps):
+        srch.batched_search_device(queries64, K, phase_events=arr)
+        torch.cuda.synchronize()
+        for i in range(6):
+            acc[i] += events[i].elapsed_time(events[i + 1]) / reps
+    n = srch.row_hi - srch.row_lo
+    nq = queries64.shape[0]
+    n0 = min(n, 8192)
+    ld_h = srch.ld_h
+    ms = acc[3] if n > n0 else acc[1]
+    rows = (n - n0) if n > n0 else n0
+    flops = 2.0 * nq * rows * srch.dim
     achieved = flops / (ms / 1e3) / 1e12
     peak = peaks["bf16_tflops"]
-    return {"bound": "tensor", "kernel": "angular_distances_kernel<4> (FP64 SIMT scan; tensor-core pass not built yet)",
+    return {"bound": "tensor", "kernel": "knn_gemm_kernel (tcgen05 fp16 UMMA, filter pass over %d rows)" % rows,
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-            "algorithmic": "2*Q*N*D flops, Q=%d N=%d D=%d per launch" % (nq, n, srch.dim),
-            "launch_ms": ms, "peak_source": peaks["source"] + " bf16 burst", "dtype": "f64"}
+            "algorithmic": "2*Q*N*D flops per launch, Q=%d N=%d D=%d" % (nq, rows, srch.dim),
+            "launch_ms": ms, "peak_source": peaks["source"] + " bf16 burst (fp16 runs on the same kind::f16 pipe)",
+            "phase_ms": {name: round(v, 4) for name, v in zip(PHASE_NAMES, acc)},
+            "candidates_per_query": {"first_pass": srch.last_stats[1] / nq, "reranked": srch.last_stats[2] / nq,
+                                     "overflowed_queries": srch.last_stats[0]},
+            "dtype": "fp16 first pass (fp32 accumulate), f64 re-rank"}
 
 
 if __name__ == "__main__":

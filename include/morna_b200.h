@@ -172,19 +172,26 @@ int morna_prepare_tensor_operand(const float *vectors, const double *pp, int64_t
  *   overflow [dev] uint8[nq]  1 where a candidate list overflowed (massive ties): those
  *                             queries hold id -1 / +inf and must be answered by morna_knn_exact
  *   stats    [dev] int32[4]   {overflowed queries, sum of first-pass survivors,
- *                              sum of re-ranked candidates, max re-ranked candidates} */
+ *                              sum of re-ranked candidates, max re-ranked candidates}
+ *   phase_events [host] NULL, or 7 cudaEvent_t recorded on `stream` at the phase boundaries
+ *                (start, queries prepared, pilot GEMM, thresholds, filter GEMM, final lists,
+ *                re-rank) so a caller can time each kernel of the step */
 size_t morna_knn_batched_workspace_bytes(int64_t n, int64_t nq, int32_t dim, int32_t k);
 int morna_knn_batched(const float *vectors, const double *pp, const void *hs, int64_t ld_h,
                       const float *rho_max, int64_t n, int32_t dim, int64_t ld, int32_t id_base,
                       const double *queries, int64_t nq, int64_t q_ld, int32_t k,
                       int32_t *out_ids, double *out_dist, uint8_t *overflow, int32_t *stats,
-                      void *workspace, size_t workspace_bytes, void *stream);
+                      void *workspace, size_t workspace_bytes, void *const *phase_events, void *stream);
 
 /* Test hook: raw fp16 tensor-core scores [nq x n] (n <= 8192) and the per-query bound eps. */
 int morna_debug_tensor_scores(const void *hs, int64_t ld_h, const float *rho_max, int64_t n, int32_t dim,
                               const double *queries, int64_t nq, int64_t q_ld, float *scores,
                               int64_t scores_ld, float *eps_out, void *workspace, size_t workspace_bytes,
                               void *stream);
+
+/* Experiment knobs (process-wide; not part of the drop-in surface): key 0 = GEMM variant
+ * (1 = CTA pairs with cta_group::2, 0 = single CTAs), key 1 = pipeline stages (4 or 6). */
+int morna_debug_set_tuning(int32_t key, int32_t value);
 
 #ifdef __cplusplus
 }

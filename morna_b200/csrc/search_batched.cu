@@ -263,6 +263,177 @@ knn_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     if (warp == 2) tmem_dealloc<1>(tmem_base, TMEM_COLS);
 }
 
+// ------------------------------------------------------------------ 2-CTA variant (cta_group::2)
+// A CTA pair owns a 256-query x 256-sample tile: CTA r holds query rows r*128.. and loads half of
+// the sample tile (rows r*128..), the leader issues M=256 UMMAs that read both CTAs' shared memory
+// and write both CTAs' TMEM.  Per-CTA shared-memory traffic drops from 48 KB to 32 KB per k-block.
+namespace gemm2 {
+constexpr int BM = 128, BN = 256, BN_HALF = 128, BK = 64, UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN_HALF * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
+constexpr int THREADS = 192;
+constexpr int ACC_STAGES = 2, TMEM_COLS = ACC_STAGES * BN;
+constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 + 256; }
+}  // namespace gemm2
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(addr));
+    return r;
+}
+
+template <int kStages>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm2::THREADS, 1)
+knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_s, GemmParams p) {
+    using namespace gemm2;
+    using namespace tc;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + kStages * STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * kStages + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * kStages + ACC_STAGES + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * kStages + 2 * ACC_STAGES);
+    volatile uint32_t *tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_q);
+        prefetch_tmap(&tmap_s);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<2>(tmem_slot, TMEM_COLS);
+        tmem_relinquish<2>();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int pair = blockIdx.x >> 1, pairs = gridDim.x >> 1;
+    const int m_pairs = (p.m_blocks + 1) >> 1;              // 256-row query blocks
+    const int total_tiles = m_pairs * p.n_tiles;
+    if (warp == 0) {
+        if (lane == 0) {     // ===== TMA producer (both CTAs); bytes are counted on the leader's barrier
+            int stage = 0; uint32_t phase = 0;
+            for (int t = pair; t < total_tiles; t += pairs) {
+                const int m_pair = t % m_pairs, n_tile = t / m_pairs;
+                const int row_q = m_pair * 2 * BM + (int)rank * BM;
+                const int row_s = p.n_begin + n_tile * BN + (int)rank * BN_HALF;
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t a_dst = base + stage * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+                    const uint32_t bar0 = mapa_rank0(full_bar(stage));
+                    if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+                    tma_load_2d_pair(a_dst, &tmap_q, bar0, kb * BK, row_q);
+                    tma_load_2d_pair(b_dst, &tmap_s, bar0, kb * BK, row_s);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {     // ===== MMA issuer: one thread of the leader CTA
+            constexpr uint32_t idesc = instr_desc_f16(2 * BM, BN, /*fp16*/ 0);
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int t = pair; t < total_tiles; t += pairs) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_src = base + stage * STAGE_BYTES, b_src = a_src + A_BYTES;
+                    const uint64_t da = smem_desc_sw128(a_src), db = smem_desc_sw128(b_src);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_f16<2>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit_pair(empty_bar(stage), 3);          // frees the stage in both CTAs
+                    if (kb == p.kblocks - 1) umma_commit_pair(tfull_bar(acc), 3);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {                 // ===== epilogue: thread = TMEM lane = query row of this CTA's half
+        const int quarter = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = pair; t < total_tiles; t += pairs) {
+            const int m_pair = t % m_pairs, n_tile = t / m_pairs;
+            const int row = m_pair * 2 * BM + (int)rank * BM + quarter * 32 + lane;
+            const bool row_ok = row < p.nq;
+            const int col_tile = p.n_begin + n_tile * BN;
+            float thr = INFINITY;
+            if (p.mode == 1 && row_ok) thr = p.thr[row];
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + c * 32, r);
+                tmem_ld_wait();
+                const int col0 = col_tile + c * 32;
+                const int valid = min(32, p.n_end - col0);
+                if (p.mode == 0) {
+                    if (row_ok && valid > 0) {
+                        float *dst = p.pilot + (int64_t)row * p.pilot_ld + (col0 - p.n_begin);
+                        if (valid == 32) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4 *>(dst + j) =
+                                    make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < valid) dst[j] = __uint_as_float(r[j]);
+                        }
+                    }
+                } else {
+                    uint32_t mask = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        mask |= (uint32_t)(__uint_as_float(r[j]) >= thr && j < valid) << j;
+                    if (mask) {
+                        int at = atomicAdd(p.cand_cnt + row, __popc(mask));
+                        float *cs = p.cand_score + (int64_t)row * p.cap;
+                        int32_t *ci = p.cand_id + (int64_t)row * p.cap;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if ((mask >> j) & 1u) {
+                                if (at < p.cap) { cs[at] = __uint_as_float(r[j]); ci[at] = p.id_base + col0 + j; }
+                                ++at;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(tempty_bar(acc), 0);       // the leader's MMA thread waits for both CTAs
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc<2>(tmem_base, TMEM_COLS);
+}
+
 // ------------------------------------------------------------------ k-th largest + filter
 constexpr int kKthThreads = 256, kKthItems = 32, kKthMax = kKthThreads * kKthItems;   // 8192 entries
 
@@ -284,91 +455,141 @@ struct KthParams {
     uint8_t *overflow; int32_t *stats;
 };
 
-// One CTA per query.  kPilot: input = the dumped pilot scores; output = thr and the pilot's
-// survivors appended to the candidate list.  !kPilot: input = candidate list; output = final list.
+// key of the kk-th largest of the keys one warp holds in registers (kItems per lane; 0 = padding)
+template <int kItems>
+__device__ __forceinline__ uint32_t warp_kth_largest(const uint32_t (&key)[kItems], int kk) {
+    uint32_t best = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t trial = best | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < kItems; ++j) c += key[j] >= trial;
+        c = __reduce_add_sync(kFull, c);
+        if (c >= kk) best = trial;
+    }
+    return best;
+}
+
+constexpr int kKwWarps = 8, kKwSlots = 32;            // one warp per query; 32 survivors per lane
+constexpr int kKwSmem = kKwWarps * 2 * 32 * kKwSlots * (int)sizeof(uint32_t);   // 64 KB
+
+// One WARP per query (8 queries per CTA, no block barriers).
+//   kPilot : input = dumped pilot scores -> thr[q] and the pilot's survivors start the candidate list
+//   !kPilot: input = candidate list      -> final candidate list
+// A pivot taken from a 512-entry sample cuts the stream to a few hundred survivors that stay in
+// lane-private shared-memory lists; the exact k-th largest a_k of the survivors (= of all entries) is
+// found with warp-wide counts, and everything >= a_k - 2 eps is written out.  If the pivot misses
+// (too few survivors, a lane list overflows, or a_k - 2 eps falls below the pivot) the warp falls
+// back to a streaming bisection over all entries, which is exact for any input.
 template <bool kPilot>
-__global__ void __launch_bounds__(kKthThreads)
-kth_filter_kernel(KthParams p) {
-    __shared__ int s_warp[kKthThreads / 32];
-    __shared__ int s_total;
-    __shared__ int s_out;
-    const int q = blockIdx.x, tid = threadIdx.x;
+__global__ void __launch_bounds__(kKwWarps * 32)
+kth_warp_kernel(KthParams p, int nq) {
+    extern __shared__ __align__(16) uint32_t kw_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = blockIdx.x * kKwWarps + warp;
+    if (q >= nq) return;
+    uint32_t *lkey = kw_smem + warp * 2 * 32 * kKwSlots;          // [slot][lane]
+    uint32_t *lidx = lkey + 32 * kKwSlots;
     int count;
     if (kPilot) count = p.n0;
     else {
         count = p.cand_cnt[q];
         if (count > p.cap) {            // survivors were dropped: the exact scan must answer this query
-            if (tid == 0) { p.overflow[q] = 1; atomicAdd(p.stats + 0, 1); p.fin_cnt[q] = 0; }
+            if (lane == 0) { p.overflow[q] = 1; atomicAdd(p.stats + 0, 1); p.fin_cnt[q] = 0; }
             return;
         }
     }
+    const float *src = kPilot ? p.pilot + (int64_t)q * p.pilot_ld : p.cand_score + (int64_t)q * p.cap;
     const int kk = min(p.k, count);
-    float score[kKthItems];
-    uint32_t key[kKthItems];
-#pragma unroll
-    for (int j = 0; j < kKthItems; ++j) {
-        int idx = j * kKthThreads + tid;
-        bool ok = idx < count;
-        float v = 0.f;
-        if (ok) v = kPilot ? p.pilot[(int64_t)q * p.pilot_ld + idx] : p.cand_score[(int64_t)q * p.cap + idx];
-        score[j] = v;
-        key[j] = ok ? float_key(v) : 0u;       // 0 sorts below every real score
-    }
-    // bitwise search for the key of the kk-th largest entry
-    uint32_t best = 0;
-    if (kk > 0) {
-        for (int bit = 31; bit >= 0; --bit) {
-            const uint32_t trial = best | (1u << bit);
-            int mine = 0;
-#pragma unroll
-            for (int j = 0; j < kKthItems; ++j) mine += key[j] >= trial;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(kFull, mine, o);
-            if ((tid & 31) == 0) s_warp[tid >> 5] = mine;
-            __syncthreads();
-            if (tid == 0) {
-                int tot = 0;
-#pragma unroll
-                for (int w = 0; w < kKthThreads / 32; ++w) tot += s_warp[w];
-                s_total = tot;
-            }
-            __syncthreads();
-            if (s_total >= kk) best = trial;
-        }
-    }
+    const int out_cap = kPilot ? p.cap : p.fcap;
     const float eps = p.eps[q];
-    // cannot prune while fewer than k scores have been seen
-    float cut = -INFINITY;
-    if (kk >= p.k) cut = __fsub_rd(key_float(best), __fmul_ru(2.0f, eps));
-    if (tid == 0) s_out = 0;
-    __syncthreads();
-    if (kPilot) {
-        if (tid == 0) p.thr[q] = cut;
+
+    uint32_t best = 0;          // key of the kk-th largest entry
+    bool lists_ok = false;      // lane lists hold every entry >= pivot
+    uint32_t pivot = 0;
+    int mine = 0;               // survivors in this lane's list
+    if (kk > 0) {
+        if (count > 32 * kKwSlots) {                 // pivot from 512 strided samples
+            uint32_t sk[16];
+            const int stride = count >> 9;
 #pragma unroll
-        for (int j = 0; j < kKthItems; ++j) {
-            int idx = j * kKthThreads + tid;
-            if (idx < count && score[j] >= cut) {
-                int at = atomicAdd(&s_out, 1);
-                if (at < p.cap) {
-                    p.cand_score[(int64_t)q * p.cap + at] = score[j];
-                    p.cand_id[(int64_t)q * p.cap + at] = p.id_base + p.n_begin + idx;
+            for (int j = 0; j < 16; ++j) sk[j] = float_key(src[(j * 32 + lane) * stride]);
+            const float want = (float)kk * 512.0f / (float)count;
+            const int r = (int)(want + 4.0f * sqrtf(want) + 4.0f);
+            pivot = r <= 512 ? warp_kth_largest<16>(sk, r) : 0u;
+        }
+        // stream: lane owns float4 groups lane, lane+32, ...; survivors go to its private list
+        const int groups = (count + 3) >> 2;
+        bool overflowed = false;
+        for (int g = lane; g < groups; g += 32) {
+            float4 v = *reinterpret_cast<const float4 *>(src + 4 * g);      // rows are 16-byte aligned and padded
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int idx = 4 * g + t;
+                const uint32_t key = float_key(vv[t]);
+                if (idx < count && key >= pivot) {
+                    if (mine < kKwSlots) { lkey[mine * 32 + lane] = key; lidx[mine * 32 + lane] = idx; }
+                    else overflowed = true;
+                    ++mine;
                 }
             }
         }
-        __syncthreads();
-        if (tid == 0) p.cand_cnt[q] = s_out;     // the filter pass appends after these
-    } else {
+        const int m = __reduce_add_sync(kFull, mine);
+        lists_ok = !__any_sync(kFull, overflowed) && m >= kk;
+        if (lists_ok) {
+            uint32_t sk[kKwSlots];
 #pragma unroll
-        for (int j = 0; j < kKthItems; ++j) {
-            int idx = j * kKthThreads + tid;
-            if (idx < count && score[j] >= cut) {
-                int at = atomicAdd(&s_out, 1);
-                if (at < p.fcap) p.fin_id[(int64_t)q * p.fcap + at] = p.cand_id[(int64_t)q * p.cap + idx];
+            for (int j = 0; j < kKwSlots; ++j) sk[j] = j < mine ? lkey[j * 32 + lane] : 0u;
+            best = warp_kth_largest<kKwSlots>(sk, kk);
+        } else {                                     // streaming bisection over every entry
+            for (int bit = 31; bit >= 0; --bit) {
+                const uint32_t trial = best | (1u << bit);
+                int c = 0;
+                for (int i = lane; i < count; i += 32) c += float_key(src[i]) >= trial;
+                c = __reduce_add_sync(kFull, c);
+                if (c >= kk) best = trial;
             }
         }
-        __syncthreads();
-        if (tid == 0) {
-            int kept = s_out;
+    }
+    // cannot prune while fewer than k scores have been seen
+    float cut = -INFINITY;
+    if (kk >= p.k) cut = __fsub_rd(key_float(best), __fmul_ru(2.0f, eps));
+    const uint32_t cut_key = cut == -INFINITY ? 0u : float_key(cut);
+    int out = 0;
+    auto emit = [&](bool keep, float score, int idx) {
+        const unsigned mask = __ballot_sync(kFull, keep);
+        const int at = out + __popc(mask & ((1u << lane) - 1u));
+        if (keep && at < out_cap) {
+            if (kPilot) {
+                p.cand_score[(int64_t)q * p.cap + at] = score;
+                p.cand_id[(int64_t)q * p.cap + at] = p.id_base + p.n_begin + idx;
+            } else {
+                p.fin_id[(int64_t)q * p.fcap + at] = p.cand_id[(int64_t)q * p.cap + idx];
+            }
+        }
+        out += __popc(mask);
+    };
+    if (lists_ok && cut_key >= pivot) {              // every entry >= cut sits in the lane lists
+        const int most = __reduce_max_sync(kFull, mine);
+        for (int j = 0; j < most; ++j) {
+            const bool have = j < mine;
+            const uint32_t key = have ? lkey[j * 32 + lane] : 0u;
+            emit(have && key >= cut_key, key_float(key), have ? (int)lidx[j * 32 + lane] : 0);
+        }
+    } else {
+        for (int i0 = 0; i0 < count; i0 += 32) {
+            const int i = i0 + lane;
+            const float v = i < count ? src[i] : 0.f;
+            emit(i < count && v >= cut, v, i);
+        }
+    }
+    if (lane == 0) {
+        if (kPilot) {
+            p.thr[q] = cut;
+            p.cand_cnt[q] = out;                     // the filter pass appends after these
+        } else {
+            int kept = out;
             if (kept > p.fcap) { p.overflow[q] = 1; atomicAdd(p.stats + 0, 1); kept = 0; }
             p.fin_cnt[q] = kept;
             atomicAdd(p.stats + 1, count);
@@ -490,13 +711,43 @@ static int sm_count_b() {
 
 constexpr int kCandCap = 4096, kFinCap = 1024, kPilotMax = kKthMax, kBatchedMaxRows = 131072;
 
+// tuning knobs for experiments (morna_debug_set_tuning): GEMM variant and pipeline depth
+static int g_gemm_pair = 1;       // 1: CTA pairs (cta_group::2), 0: single CTAs
+static int g_gemm_stages = 6;
+
+static int launch_knn_gemm(const CUtensorMap &tmap_q, const CUtensorMap &tmap_s, const GemmParams &gp, cudaStream_t s) {
+    if (!g_gemm_pair) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            MORNA_CUDA_TRY(cudaFuncSetAttribute(knn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                gemm::SMEM_BYTES));
+            attr_set = true;
+        }
+        int tiles = gp.m_blocks * gp.n_tiles;
+        int grid = tiles < sm_count_b() ? tiles : sm_count_b();
+        knn_gemm_kernel<<<grid, gemm::THREADS, gemm::SMEM_BYTES, s>>>(tmap_q, tmap_s, gp);
+        MORNA_LAUNCH_CHECK();
+        return MORNA_OK;
+    }
+    const int stages = g_gemm_stages == 4 ? 4 : 6;
+    auto kern = stages == 4 ? knn_gemm2_kernel<4> : knn_gemm2_kernel<6>;
+    const int smem = gemm2::smem_bytes(stages);
+    MORNA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int tiles = ((gp.m_blocks + 1) / 2) * gp.n_tiles;
+    int pairs = sm_count_b() / 2;
+    if (tiles < pairs) pairs = tiles;
+    kern<<<2 * pairs, gemm2::THREADS, smem, s>>>(tmap_q, tmap_s, gp);
+    MORNA_LAUNCH_CHECK();
+    return MORNA_OK;
+}
+
 struct BatchWs {
     size_t hq, qq, eps, pilot, thr, cand_score, cand_id, cand_cnt, fin_id, fin_cnt, total;
     int64_t nq_pad, n0, pilot_ld;
 };
 static BatchWs batch_ws_layout(int64_t n, int64_t nq, int64_t ld_h) {
     BatchWs w{};
-    w.nq_pad = (nq + gemm::BM - 1) / gemm::BM * gemm::BM;
+    w.nq_pad = (nq + 2 * gemm::BM - 1) / (2 * gemm::BM) * (2 * gemm::BM);      // CTA pairs own 256 query rows
     w.n0 = n < kPilotMax ? n : kPilotMax;
     w.pilot_ld = (w.n0 + 3) / 4 * 4;
     size_t off = 0;
@@ -546,7 +797,7 @@ extern "C" int morna_knn_batched(const float *vectors, const double *pp, const v
                                  const float *rho_max, int64_t n, int32_t dim, int64_t ld, int32_t id_base,
                                  const double *queries, int64_t nq, int64_t q_ld, int32_t k, int32_t *out_ids,
                                  double *out_dist, uint8_t *overflow, int32_t *stats, void *workspace,
-                                 size_t workspace_bytes, void *stream) {
+                                 size_t workspace_bytes, void *const *phase_events, void *stream) {
     if (!vectors || !pp || !hs || !rho_max || !queries || !out_ids || !out_dist || !overflow || !stats ||
         n <= 0 || n > kBatchedMaxRows || nq <= 0 || dim <= 0 || ld < dim || (ld & 3) || q_ld < dim || k <= 0 ||
         k > kFinCap / 2 || ld_h != morna_tensor_operand_ld(dim))
@@ -566,6 +817,9 @@ extern "C" int morna_knn_batched(const float *vectors, const double *pp, const v
     int32_t *fin_id = (int32_t *)(ws + w.fin_id);
     int32_t *fin_cnt = (int32_t *)(ws + w.fin_cnt);
 
+    int phase = 0;
+    auto mark = [&]() { if (phase_events) cudaEventRecord((cudaEvent_t)phase_events[phase], s); ++phase; };
+    mark();                                                      // 0: start
     MORNA_CUDA_TRY(cudaMemsetAsync(overflow, 0, (size_t)nq, s));
     MORNA_CUDA_TRY(cudaMemsetAsync(stats, 0, 4 * sizeof(int32_t), s));
     MORNA_CUDA_TRY(cudaMemsetAsync(cand_cnt, 0, (size_t)nq * sizeof(int32_t), s));
@@ -581,17 +835,12 @@ extern "C" int morna_knn_batched(const float *vectors, const double *pp, const v
         MORNA_LAUNCH_CHECK();
     }
 
+    mark();                                                      // 1: queries prepared
     CUtensorMap tmap_q, tmap_s;
     int rc = make_tmap(&tmap_q, hq, (uint64_t)w.nq_pad, (uint64_t)ld_h, gemm::BM);
     if (rc != MORNA_OK) return rc;
-    rc = make_tmap(&tmap_s, hs, (uint64_t)n, (uint64_t)ld_h, gemm::BN);
+    rc = make_tmap(&tmap_s, hs, (uint64_t)n, (uint64_t)ld_h, g_gemm_pair ? gemm2::BN_HALF : gemm::BN);
     if (rc != MORNA_OK) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MORNA_CUDA_TRY(cudaFuncSetAttribute(knn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            gemm::SMEM_BYTES));
-        attr_set = true;
-    }
     GemmParams gp{};
     gp.nq = (int32_t)nq; gp.kblocks = (int32_t)(ld_h / gemm::BK); gp.m_blocks = (int32_t)(w.nq_pad / gemm::BM);
     gp.cap = kCandCap; gp.id_base = id_base; gp.pilot = pilot; gp.pilot_ld = w.pilot_ld; gp.thr = thr;
@@ -599,11 +848,7 @@ extern "C" int morna_knn_batched(const float *vectors, const double *pp, const v
     auto launch_gemm = [&](int32_t n_begin, int32_t n_end, int32_t mode) -> int {
         gp.n_begin = n_begin; gp.n_end = n_end; gp.mode = mode;
         gp.n_tiles = (n_end - n_begin + gemm::BN - 1) / gemm::BN;
-        int tiles = gp.m_blocks * gp.n_tiles;
-        int grid = tiles < sm_count_b() ? tiles : sm_count_b();
-        knn_gemm_kernel<<<grid, gemm::THREADS, gemm::SMEM_BYTES, s>>>(tmap_q, tmap_s, gp);
-        MORNA_LAUNCH_CHECK();
-        return MORNA_OK;
+        return launch_knn_gemm(tmap_q, tmap_s, gp, s);
     };
 
     KthParams kp{};
@@ -614,14 +859,21 @@ extern "C" int morna_knn_batched(const float *vectors, const double *pp, const v
 
     rc = launch_gemm(0, (int32_t)w.n0, 0);                       // pilot block: dump scores
     if (rc != MORNA_OK) return rc;
-    kth_filter_kernel<true><<<(unsigned)nq, kKthThreads, 0, s>>>(kp);
+    mark();                                                      // 2: pilot GEMM
+    MORNA_CUDA_TRY(cudaFuncSetAttribute(kth_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKwSmem));
+    MORNA_CUDA_TRY(cudaFuncSetAttribute(kth_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKwSmem));
+    const unsigned kth_grid = (unsigned)((nq + kKwWarps - 1) / kKwWarps);
+    kth_warp_kernel<true><<<kth_grid, kKwWarps * 32, kKwSmem, s>>>(kp, (int)nq);
     MORNA_LAUNCH_CHECK();
+    mark();                                                      // 3: thresholds
     if (w.n0 < n) {
         rc = launch_gemm((int32_t)w.n0, (int32_t)n, 1);          // the rest: keep scores above thr
         if (rc != MORNA_OK) return rc;
     }
-    kth_filter_kernel<false><<<(unsigned)nq, kKthThreads, 0, s>>>(kp);
+    mark();                                                      // 4: filter GEMM
+    kth_warp_kernel<false><<<kth_grid, kKwWarps * 32, kKwSmem, s>>>(kp, (int)nq);
     MORNA_LAUNCH_CHECK();
+    mark();                                                      // 5: final candidate lists
     const size_t rr_smem = (size_t)ld * sizeof(double) + (size_t)kFinCap * (sizeof(double) + sizeof(int));
     if (rr_smem > 200 * 1024) return MORNA_ERR_INVALID_ARGUMENT;
     if (rr_smem > 48 * 1024)
@@ -631,6 +883,7 @@ extern "C" int morna_knn_batched(const float *vectors, const double *pp, const v
                                                                       fin_id, fin_cnt, overflow, kFinCap, k, out_ids,
                                                                       out_dist);
     MORNA_LAUNCH_CHECK();
+    mark();                                                      // 6: re-rank + order
     return MORNA_OK;
 }
 
@@ -657,16 +910,20 @@ extern "C" int morna_debug_tensor_scores(const void *hs, int64_t ld_h, const flo
     CUtensorMap tmap_q, tmap_s;
     int rc = make_tmap(&tmap_q, hq, (uint64_t)w.nq_pad, (uint64_t)ld_h, gemm::BM);
     if (rc != MORNA_OK) return rc;
-    rc = make_tmap(&tmap_s, hs, (uint64_t)n, (uint64_t)ld_h, gemm::BN);
+    rc = make_tmap(&tmap_s, hs, (uint64_t)n, (uint64_t)ld_h, g_gemm_pair ? gemm2::BN_HALF : gemm::BN);
     if (rc != MORNA_OK) return rc;
-    MORNA_CUDA_TRY(cudaFuncSetAttribute(knn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
     GemmParams gp{};
     gp.nq = (int32_t)nq; gp.kblocks = (int32_t)(ld_h / gemm::BK); gp.m_blocks = (int32_t)(w.nq_pad / gemm::BM);
     gp.n_begin = 0; gp.n_end = (int32_t)n; gp.mode = 0; gp.pilot = scores; gp.pilot_ld = scores_ld;
     gp.n_tiles = (gp.n_end + gemm::BN - 1) / gemm::BN;
-    int tiles = gp.m_blocks * gp.n_tiles;
-    int grid = tiles < sm_count_b() ? tiles : sm_count_b();
-    knn_gemm_kernel<<<grid, gemm::THREADS, gemm::SMEM_BYTES, s>>>(tmap_q, tmap_s, gp);
-    MORNA_LAUNCH_CHECK();
+    return launch_knn_gemm(tmap_q, tmap_s, gp, s);
+}
+
+/* Experiment knobs, process-wide: key 0 = GEMM variant (1 CTA pairs / 0 single CTA),
+ * key 1 = shared-memory pipeline stages of the pair variant (4 or 6). */
+extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
+    if (key == 0) g_gemm_pair = value ? 1 : 0;
+    else if (key == 1) g_gemm_stages = value;
+    else return MORNA_ERR_INVALID_ARGUMENT;
     return MORNA_OK;
 }

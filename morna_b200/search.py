@@ -14,6 +14,18 @@ from . import _lib, files
 from .index import round_up
 
 
+PHASE_NAMES = ("prep_queries", "gemm_pilot", "kth_pilot", "gemm_filter", "kth_final", "rerank_select")
+
+
+def make_phase_events():
+    """Seven CUDA events for morna_knn_batched's phase boundaries: (events, ctypes array)."""
+    import ctypes
+    events = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+    for e in events:
+        e.record()                      # creates the underlying cudaEvent_t
+    return events, (ctypes.c_void_p * 7)(*[e.cuda_event for e in events])
+
+
 class MornaSearch(object):
     def __init__(self, basename=None, device=None, shard=None, vectors=None, stats=None,
                  sample_frequencies=None, internal_id_map=None):
@@ -162,7 +174,7 @@ class MornaSearch(object):
         self._bws = None
         self.last_stats = None
 
-    def batched_search_device(self, queries, k, stream=None, check_overflow=True):
+    def batched_search_device(self, queries, k, stream=None, check_overflow=True, phase_events=None):
         """Same contract and same results as exact_search_device, with the N x D
         contraction on the tensor cores (fp16 first pass with a rigorous error bound,
         FP64 re-rank).  Queries whose candidate lists overflow (massive ties) are
@@ -193,7 +205,7 @@ class MornaSearch(object):
                     self.ld_h, _lib.dev_ptr(self.rho_max), b1 - b0, self.dim, self.ld, self.row_lo + b0,
                     _lib.ptr(queries), nq, self.dim, k, _lib.dev_ptr(out_ids), _lib.dev_ptr(out_d),
                     _lib.dev_ptr(overflow), _lib.dev_ptr(stats), _lib.dev_ptr(self._bws), self._bws.numel(),
-                    _lib.stream_ptr(stream)), "morna_knn_batched")
+                    phase_events, _lib.stream_ptr(stream)), "morna_knn_batched")
                 if check_overflow:
                     st = stats.cpu()
                     stats_total += st.to(torch.int64)

@@ -96,6 +96,28 @@ def test_batched_equals_exact_scan_bit_for_bit(n, d, nq, k):
     print("stats", srch.last_stats, "per query survivors %.1f final %.1f" % (srch.last_stats[1] / nq, srch.last_stats[2] / nq))
 
 
+@pytest.mark.parametrize("pair,stages", [(1, 6), (1, 4), (0, 4)])
+def test_gemm_variants_agree(pair, stages):
+    """CTA-pair (cta_group::2) and single-CTA GEMM variants give the same exact results."""
+    from morna_b200 import _lib
+    lib = _lib.load()
+    try:
+        assert lib.morna_debug_set_tuning(0, pair) == 0 and lib.morna_debug_set_tuning(1, stages) == 0
+        rng = np.random.default_rng(77)
+        n, d, nq, k = 17000, 1000, 700, 64
+        S = rng.standard_normal((n, d)).astype(np.float32)
+        srch = make_search(S)
+        Q = S[rng.permutation(n)[:nq]].astype(np.float64) + 0.02 * rng.standard_normal((nq, d))
+        q = torch.from_numpy(Q).cuda()
+        e_ids, e_d = srch.exact_search_device(q, k)
+        b_ids, b_d = srch.batched_search_device(q, k)
+        assert srch.last_stats[0] == 0
+        assert torch.equal(b_ids, e_ids) and torch.equal(b_d, e_d)
+    finally:
+        lib.morna_debug_set_tuning(0, 1)
+        lib.morna_debug_set_tuning(1, 6)
+
+
 def test_batched_with_massive_ties_falls_back_to_exact_scan():
     oracle = mo.go_index(tiny_lines(), features=3000, sample_threshold=100)
     S = oracle.matrix_f32()
