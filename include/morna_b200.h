@@ -183,6 +183,20 @@ int morna_knn_batched(const float *vectors, const double *pp, const void *hs, in
                       int32_t *out_ids, double *out_dist, uint8_t *overflow, int32_t *stats,
                       void *workspace, size_t workspace_bytes, void *const *phase_events, void *stream);
 
+/* The two halves of morna_knn_batched, for callers that pipeline consecutive batches on two
+ * streams (the scoring half is tensor-core bound, the re-rank half HBM-gather bound, and their
+ * kernels are sized to share an SM).  morna_knn_batched_score leaves each query's candidate list
+ * in `workspace`; morna_knn_batched_rerank must be given the same workspace, queries, n, nq, k and
+ * overflow array and be ordered after it (same stream, or an event). */
+int morna_knn_batched_score(const void *hs, int64_t ld_h, const float *rho_max, int64_t n, int32_t dim,
+                            int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
+                            uint8_t *overflow, int32_t *stats, void *workspace, size_t workspace_bytes,
+                            void *const *phase_events, void *stream);
+int morna_knn_batched_rerank(const float *vectors, const double *pp, int64_t n, int32_t dim, int64_t ld,
+                             int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
+                             int32_t *out_ids, double *out_dist, const uint8_t *overflow, void *workspace,
+                             size_t workspace_bytes, void *stream);
+
 /* Test hook: raw fp16 tensor-core scores [nq x n] (n <= 8192) and the per-query bound eps. */
 int morna_debug_tensor_scores(const void *hs, int64_t ld_h, const float *rho_max, int64_t n, int32_t dim,
                               const double *queries, int64_t nq, int64_t q_ld, float *scores,

@@ -52,6 +52,10 @@ _SIGNATURES = {
     "morna_knn_batched_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_i32, _c_i32]),
     "morna_knn_batched": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_i32, _c_i64, _c_i32,
                                          _c_vp, _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_vp, _c_vp]),
+    "morna_knn_batched_score": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp, _c_i64, _c_i64, _c_i32,
+                                               _c_vp, _c_vp, _c_vp, _c_sz, _c_vp, _c_vp]),
+    "morna_knn_batched_rerank": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i32, _c_i64, _c_i32, _c_vp, _c_i64, _c_i64, _c_i32,
+                                                _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_vp]),
     "morna_debug_tensor_scores": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_i64, _c_i32, _c_vp, _c_i64, _c_i64, _c_vp,
                                                  _c_i64, _c_vp, _c_vp, _c_sz, _c_vp]),
     "morna_debug_set_tuning": (ctypes.c_int, [_c_i32, _c_i32]),

@@ -600,69 +600,89 @@ kth_warp_kernel(KthParams p, int nq) {
 }
 
 // ------------------------------------------------------------------ exact re-rank + final order
-constexpr int kRerankThreads = 256;
+constexpr int kRerankThreads = 512;
 
-// One CTA per query: FP64 distances of its candidates (canonical sums), then a bitonic sort
-// under the reference order and the first k written out.
+// Persistent CTAs (two per SM), each loops over queries: FP64 distances of the query's candidates
+// with the canonical sums (one warp per candidate row, four 16-byte loads in flight per lane), then
+// a bitonic sort under the reference order and the first k written out.  HBM-gather bound:
+// candidates * 4 * ld bytes per query.  Small enough (40 KB smem, 40 registers) to share an SM with
+// the GEMM CTA of the next query chunk.
 __global__ void __launch_bounds__(kRerankThreads)
 rerank_select_kernel(const float *__restrict__ vectors, const double *__restrict__ pp, int64_t ld, int32_t dim,
                      int32_t id_base, const double *__restrict__ queries, int64_t q_ld,
                      const double *__restrict__ qq, const int32_t *__restrict__ fin_id,
                      const int32_t *__restrict__ fin_cnt, const uint8_t *__restrict__ overflow, int32_t fcap,
-                     int32_t k, int32_t *__restrict__ out_ids, double *__restrict__ out_dist) {
+                     int32_t k, int32_t nq, int32_t *__restrict__ out_ids, double *__restrict__ out_dist) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *qs = reinterpret_cast<double *>(smem_raw);                 // [ld]
     double *sd = qs + ld;                                              // [fcap]
     int *si = reinterpret_cast<int *>(sd + fcap);                      // [fcap]
-    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int32_t *oi = out_ids + (int64_t)q * k;
-    double *od = out_dist + (int64_t)q * k;
-    if (overflow[q]) {                   // answered by the exact scan afterwards
-        for (int i = tid; i < k; i += kRerankThreads) { oi[i] = -1; od[i] = INFINITY; }
-        return;
-    }
-    const int count = min(fin_cnt[q], fcap);
-    for (int c = tid; c < ld; c += kRerankThreads) qs[c] = c < dim ? queries[(int64_t)q * q_ld + c] : 0.0;
-    int P = 32;
-    while (P < count) P <<= 1;
-    for (int i = tid; i < P; i += kRerankThreads) { sd[i] = INFINITY; si[i] = -1; }
-    __syncthreads();
-    const double qqv = qq[q];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int chunks = (int)(ld >> 2);
-    for (int i = warp; i < count; i += kRerankThreads / 32) {
-        const int id = fin_id[(int64_t)q * fcap + i];
-        const int64_t row = id - id_base;
-        const float4 *src = reinterpret_cast<const float4 *>(vectors + row * ld);
-        double acc = 0.0;
-        for (int c = lane; c < chunks; c += 32) {
-            float4 v = __ldg(src + c);
-            double2 qa = *reinterpret_cast<const double2 *>(qs + 4 * c);
-            double2 qb = *reinterpret_cast<const double2 *>(qs + 4 * c + 2);
-            acc = fma((double)v.x, qa.x, acc); acc = fma((double)v.y, qa.y, acc);
-            acc = fma((double)v.z, qb.x, acc); acc = fma((double)v.w, qb.y, acc);
+    for (int q = blockIdx.x; q < nq; q += gridDim.x) {
+        int32_t *oi = out_ids + (int64_t)q * k;
+        double *od = out_dist + (int64_t)q * k;
+        if (overflow[q]) {               // answered by the exact scan afterwards
+            for (int i = tid; i < k; i += kRerankThreads) { oi[i] = -1; od[i] = INFINITY; }
+            continue;
         }
-        acc = warp_sum(acc);
-        if (lane == 0) { sd[i] = angular_from_sums(pp[row], qqv, acc); si[i] = id; }
-    }
-    // bitonic sort of P entries under `before`
-    for (int size = 2; size <= P; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            __syncthreads();
-            for (int i = tid; i < (P >> 1); i += kRerankThreads) {
-                int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
-                bool asc = (lo & size) == 0;
-                double dl = sd[lo], dh = sd[hi];
-                int il = si[lo], ih = si[hi];
-                bool swap = asc ? before(dh, ih, dl, il) : before(dl, il, dh, ih);
-                if (swap) { sd[lo] = dh; sd[hi] = dl; si[lo] = ih; si[hi] = il; }
+        const int count = min(fin_cnt[q], fcap);
+        __syncthreads();                 // previous query's sort buffers are free
+        for (int c = tid; c < ld; c += kRerankThreads) qs[c] = c < dim ? queries[(int64_t)q * q_ld + c] : 0.0;
+        int P = 32;
+        while (P < count) P <<= 1;
+        for (int i = tid; i < P; i += kRerankThreads) { sd[i] = INFINITY; si[i] = -1; }
+        __syncthreads();
+        const double qqv = qq[q];
+        for (int i = warp; i < count; i += kRerankThreads / 32) {
+            const int id = fin_id[(int64_t)q * fcap + i];
+            const int64_t row = id - id_base;
+            const float4 *src = reinterpret_cast<const float4 *>(vectors + row * ld);
+            double acc = 0.0;
+            int c = lane;
+            for (; c + 96 < chunks; c += 128) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = ldg_stream_f4(src + c + 32 * u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double *qp = qs + 4 * (c + 32 * u);
+                    double2 qa = *reinterpret_cast<const double2 *>(qp);
+                    double2 qb = *reinterpret_cast<const double2 *>(qp + 2);
+                    acc = fma((double)v[u].x, qa.x, acc); acc = fma((double)v[u].y, qa.y, acc);
+                    acc = fma((double)v[u].z, qb.x, acc); acc = fma((double)v[u].w, qb.y, acc);
+                }
+            }
+            for (; c < chunks; c += 32) {
+                float4 v = ldg_stream_f4(src + c);
+                double2 qa = *reinterpret_cast<const double2 *>(qs + 4 * c);
+                double2 qb = *reinterpret_cast<const double2 *>(qs + 4 * c + 2);
+                acc = fma((double)v.x, qa.x, acc); acc = fma((double)v.y, qa.y, acc);
+                acc = fma((double)v.z, qb.x, acc); acc = fma((double)v.w, qb.y, acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) { sd[i] = angular_from_sums(pp[row], qqv, acc); si[i] = id; }
+        }
+        // bitonic sort of P entries under `before`
+        for (int size = 2; size <= P; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                __syncthreads();
+                for (int i = tid; i < (P >> 1); i += kRerankThreads) {
+                    int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                    bool asc = (lo & size) == 0;
+                    double dl = sd[lo], dh = sd[hi];
+                    int il = si[lo], ih = si[hi];
+                    bool swap = asc ? before(dh, ih, dl, il) : before(dl, il, dh, ih);
+                    if (swap) { sd[lo] = dh; sd[hi] = dl; si[lo] = ih; si[hi] = il; }
+                }
             }
         }
-    }
-    __syncthreads();
-    for (int i = tid; i < k; i += kRerankThreads) {
-        bool ok = i < count && i < P && si[i] >= 0;
-        oi[i] = ok ? si[i] : -1;
-        od[i] = ok ? sd[i] : INFINITY;
+        __syncthreads();
+        for (int i = tid; i < k; i += kRerankThreads) {
+            bool ok = i < count && i < P && si[i] >= 0;
+            oi[i] = ok ? si[i] : -1;
+            od[i] = ok ? sd[i] : INFINITY;
+        }
     }
 }
 
@@ -713,7 +733,8 @@ constexpr int kCandCap = 4096, kFinCap = 1024, kPilotMax = kKthMax, kBatchedMaxR
 
 // tuning knobs for experiments (morna_debug_set_tuning): GEMM variant and pipeline depth
 static int g_gemm_pair = 1;       // 1: CTA pairs (cta_group::2), 0: single CTAs
-static int g_gemm_stages = 6;
+static int g_gemm_stages = 4;
+
 
 static int launch_knn_gemm(const CUtensorMap &tmap_q, const CUtensorMap &tmap_s, const GemmParams &gp, cudaStream_t s) {
     if (!g_gemm_pair) {
@@ -793,14 +814,14 @@ extern "C" size_t morna_knn_batched_workspace_bytes(int64_t n, int64_t nq, int32
     return batch_ws_layout(n, nq, morna_tensor_operand_ld(dim)).total;
 }
 
-extern "C" int morna_knn_batched(const float *vectors, const double *pp, const void *hs, int64_t ld_h,
-                                 const float *rho_max, int64_t n, int32_t dim, int64_t ld, int32_t id_base,
-                                 const double *queries, int64_t nq, int64_t q_ld, int32_t k, int32_t *out_ids,
-                                 double *out_dist, uint8_t *overflow, int32_t *stats, void *workspace,
-                                 size_t workspace_bytes, void *const *phase_events, void *stream) {
-    if (!vectors || !pp || !hs || !rho_max || !queries || !out_ids || !out_dist || !overflow || !stats ||
-        n <= 0 || n > kBatchedMaxRows || nq <= 0 || dim <= 0 || ld < dim || (ld & 3) || q_ld < dim || k <= 0 ||
-        k > kFinCap / 2 || ld_h != morna_tensor_operand_ld(dim))
+// Scoring half of morna_knn_batched: fp16 tensor-core scores, thresholds and the final candidate
+// lists of every query, left in the workspace (tensor-core bound; touches HBM lightly).
+extern "C" int morna_knn_batched_score(const void *hs, int64_t ld_h, const float *rho_max, int64_t n, int32_t dim,
+                                       int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
+                                       uint8_t *overflow, int32_t *stats, void *workspace, size_t workspace_bytes,
+                                       void *const *phase_events, void *stream) {
+    if (!hs || !rho_max || !queries || !overflow || !stats || n <= 0 || n > kBatchedMaxRows || nq <= 0 || dim <= 0 ||
+        q_ld < dim || k <= 0 || k > kFinCap / 2 || ld_h != morna_tensor_operand_ld(dim))
         return MORNA_ERR_INVALID_ARGUMENT;
     BatchWs w = batch_ws_layout(n, nq, ld_h);
     if (!workspace || workspace_bytes < w.total) return MORNA_ERR_WORKSPACE_TOO_SMALL;
@@ -834,7 +855,6 @@ extern "C" int morna_knn_batched(const float *vectors, const double *pp, const v
                                                                     eps, rho_max, eps_acc);
         MORNA_LAUNCH_CHECK();
     }
-
     mark();                                                      // 1: queries prepared
     CUtensorMap tmap_q, tmap_s;
     int rc = make_tmap(&tmap_q, hq, (uint64_t)w.nq_pad, (uint64_t)ld_h, gemm::BM);
@@ -850,19 +870,18 @@ extern "C" int morna_knn_batched(const float *vectors, const double *pp, const v
         gp.n_tiles = (n_end - n_begin + gemm::BN - 1) / gemm::BN;
         return launch_knn_gemm(tmap_q, tmap_s, gp, s);
     };
-
     KthParams kp{};
     kp.k = k; kp.n0 = (int32_t)w.n0; kp.n_begin = 0; kp.id_base = id_base; kp.cap = kCandCap; kp.fcap = kFinCap;
     kp.pilot = pilot; kp.pilot_ld = w.pilot_ld; kp.eps = eps; kp.thr = thr; kp.cand_score = cand_score;
     kp.cand_id = cand_id; kp.cand_cnt = cand_cnt; kp.fin_id = fin_id; kp.fin_cnt = fin_cnt; kp.overflow = overflow;
     kp.stats = stats;
+    MORNA_CUDA_TRY(cudaFuncSetAttribute(kth_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKwSmem));
+    MORNA_CUDA_TRY(cudaFuncSetAttribute(kth_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKwSmem));
+    const unsigned kth_grid = (unsigned)((nq + kKwWarps - 1) / kKwWarps);
 
     rc = launch_gemm(0, (int32_t)w.n0, 0);                       // pilot block: dump scores
     if (rc != MORNA_OK) return rc;
     mark();                                                      // 2: pilot GEMM
-    MORNA_CUDA_TRY(cudaFuncSetAttribute(kth_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKwSmem));
-    MORNA_CUDA_TRY(cudaFuncSetAttribute(kth_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKwSmem));
-    const unsigned kth_grid = (unsigned)((nq + kKwWarps - 1) / kKwWarps);
     kth_warp_kernel<true><<<kth_grid, kKwWarps * 32, kKwSmem, s>>>(kp, (int)nq);
     MORNA_LAUNCH_CHECK();
     mark();                                                      // 3: thresholds
@@ -874,17 +893,51 @@ extern "C" int morna_knn_batched(const float *vectors, const double *pp, const v
     kth_warp_kernel<false><<<kth_grid, kKwWarps * 32, kKwSmem, s>>>(kp, (int)nq);
     MORNA_LAUNCH_CHECK();
     mark();                                                      // 5: final candidate lists
+    return MORNA_OK;
+}
+
+// Re-rank half: exact FP64 distances of the candidate lists a previous morna_knn_batched_score left
+// in the same workspace, ordered under the reference rule (HBM-gather bound; no tensor cores).
+extern "C" int morna_knn_batched_rerank(const float *vectors, const double *pp, int64_t n, int32_t dim, int64_t ld,
+                                        int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
+                                        int32_t *out_ids, double *out_dist, const uint8_t *overflow, void *workspace,
+                                        size_t workspace_bytes, void *stream) {
+    if (!vectors || !pp || !queries || !out_ids || !out_dist || !overflow || n <= 0 || n > kBatchedMaxRows ||
+        nq <= 0 || dim <= 0 || ld < dim || (ld & 3) || q_ld < dim || k <= 0 || k > kFinCap / 2)
+        return MORNA_ERR_INVALID_ARGUMENT;
+    BatchWs w = batch_ws_layout(n, nq, morna_tensor_operand_ld(dim));
+    if (!workspace || workspace_bytes < w.total) return MORNA_ERR_WORKSPACE_TOO_SMALL;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned char *ws = (unsigned char *)workspace;
+    const double *qq = (const double *)(ws + w.qq);
+    const int32_t *fin_id = (const int32_t *)(ws + w.fin_id);
+    const int32_t *fin_cnt = (const int32_t *)(ws + w.fin_cnt);
     const size_t rr_smem = (size_t)ld * sizeof(double) + (size_t)kFinCap * (sizeof(double) + sizeof(int));
     if (rr_smem > 200 * 1024) return MORNA_ERR_INVALID_ARGUMENT;
     if (rr_smem > 48 * 1024)
         MORNA_CUDA_TRY(cudaFuncSetAttribute(rerank_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)rr_smem));
-    rerank_select_kernel<<<(unsigned)nq, kRerankThreads, rr_smem, s>>>(vectors, pp, ld, dim, id_base, queries, q_ld, qq,
-                                                                      fin_id, fin_cnt, overflow, kFinCap, k, out_ids,
-                                                                      out_dist);
+    const unsigned rr_grid = (unsigned)(nq < 2 * sm_count_b() ? nq : 2 * sm_count_b());
+    rerank_select_kernel<<<rr_grid, kRerankThreads, rr_smem, s>>>(vectors, pp, ld, dim, id_base, queries, q_ld, qq,
+                                                                  fin_id, fin_cnt, overflow, kFinCap, k, (int32_t)nq,
+                                                                  out_ids, out_dist);
     MORNA_LAUNCH_CHECK();
-    mark();                                                      // 6: re-rank + order
     return MORNA_OK;
+}
+
+extern "C" int morna_knn_batched(const float *vectors, const double *pp, const void *hs, int64_t ld_h,
+                                 const float *rho_max, int64_t n, int32_t dim, int64_t ld, int32_t id_base,
+                                 const double *queries, int64_t nq, int64_t q_ld, int32_t k, int32_t *out_ids,
+                                 double *out_dist, uint8_t *overflow, int32_t *stats, void *workspace,
+                                 size_t workspace_bytes, void *const *phase_events, void *stream) {
+    if (!vectors || !pp || !out_ids || !out_dist || ld < dim || (ld & 3)) return MORNA_ERR_INVALID_ARGUMENT;
+    int rc = morna_knn_batched_score(hs, ld_h, rho_max, n, dim, id_base, queries, nq, q_ld, k, overflow, stats,
+                                     workspace, workspace_bytes, phase_events, stream);
+    if (rc != MORNA_OK) return rc;
+    rc = morna_knn_batched_rerank(vectors, pp, n, dim, ld, id_base, queries, nq, q_ld, k, out_ids, out_dist, overflow,
+                                  workspace, workspace_bytes, stream);
+    if (rc == MORNA_OK && phase_events) cudaEventRecord((cudaEvent_t)phase_events[6], (cudaStream_t)stream);
+    return rc;
 }
 
 // Raw fp16 tensor-core scores of a query block against the first n0 samples, plus the
@@ -924,6 +977,7 @@ extern "C" int morna_debug_tensor_scores(const void *hs, int64_t ld_h, const flo
 extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
     if (key == 0) g_gemm_pair = value ? 1 : 0;
     else if (key == 1) g_gemm_stages = value;
+
     else return MORNA_ERR_INVALID_ARGUMENT;
     return MORNA_OK;
 }

@@ -1,4 +1,4 @@
-"""Phase timings of the batched path at the headline shape, for each GEMM variant."""
+"""Timings of the batched path at the headline shape: phases (single stream) and pipelined totals."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -12,24 +12,32 @@ rows = torch.randperm(50000)[:4096].cuda()
 q = S[rows].double()
 s.enable_tensor_path()
 e_ids, e_d = s.exact_search_device(q[:256], 100)
-variants = [(1, 6), (1, 4), (0, 4)] if len(sys.argv) < 2 else [tuple(int(x) for x in a.split(',')) for a in sys.argv[1:]]
-for pair, stages in variants:
-    lib.morna_debug_set_tuning(0, pair); lib.morna_debug_set_tuning(1, stages)
-    events, arr = make_phase_events()
+
+def timed(reps=10, **kw):
     for i in range(3):
-        ids, d = s.batched_search_device(q, 100, phase_events=arr)
+        ids, d = s.batched_search_device(q, 100, **kw)
     torch.cuda.synchronize()
     ok = bool(torch.equal(e_ids, ids[:256])) and bool(torch.equal(e_d, d[:256]))
-    acc = [0.0] * 6
-    reps = 10
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    tot = 0.0
+    e0.record()
     for i in range(reps):
-        e0.record()
-        s.batched_search_device(q, 100, phase_events=arr)
-        e1.record(); torch.cuda.synchronize()
-        tot += e0.elapsed_time(e1) / reps
+        s.batched_search_device(q, 100, **kw)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, ok
+
+events, arr = make_phase_events()
+acc = [0.0] * 6
+for i in range(5):
+    s.batched_search_device(q, 100, phase_events=arr, pipelined=False)
+    torch.cuda.synchronize()
+    if i >= 2:
         for j in range(6):
-            acc[j] += events[j].elapsed_time(events[j + 1]) / reps
-    print("pair=%d stages=%d equal=%s total %.3f ms | " % (pair, stages, ok, tot) +
-          " ".join("%s %.3f" % (n, v) for n, v in zip(PHASE_NAMES, acc)), "| stats", s.last_stats)
+            acc[j] += events[j].elapsed_time(events[j + 1]) / 3
+print("phases (single stream): " + " ".join("%s %.3f" % (n, v) for n, v in zip(PHASE_NAMES, acc)), "| stats", s.last_stats)
+print("single stream: %.3f ms equal=%s" % timed(pipelined=False))
+for chunk in (512, 1024, 2048):
+    lib.morna_debug_set_tuning(2, chunk)
+    print("pipelined chunk=%d: %.3f ms equal=%s" % ((chunk,) + timed(pipelined=True)))
+print("pipelined, no overflow check chunk=1024:", end=" ")
+lib.morna_debug_set_tuning(2, 1024)
+print("%.3f ms equal=%s" % timed(pipelined=True, check_overflow=False))
