@@ -152,6 +152,17 @@ int morna_knn_exact(const float *vectors, const double *pp, int64_t n, int32_t d
                     int32_t *out_ids, double *out_dist,
                     void *workspace, size_t workspace_bytes, void *stream);
 
+/* exact_search_nn for ONE query, HBM-bound: an FP32 scan streams the rows once (4*n*ld bytes), the
+ * rows whose FP32 score is within a rigorous rounding bound of the k-th best are re-ranked with
+ * the FP64 sums of morna_knn_exact, so ids and distances are identical to it.
+ *   query    [dev] double[dim]
+ *   fallback [dev] int32[1]  out: 1 if ties overflowed the candidate list (outputs then hold
+ *                            nothing valid and morna_knn_exact must answer), else 0 */
+size_t morna_knn_single_workspace_bytes(int64_t n);
+int morna_knn_single(const float *vectors, const double *pp, int64_t n, int32_t dim, int64_t ld,
+                     int32_t id_base, const double *query, int32_t k, int32_t *out_ids, double *out_dist,
+                     int32_t *fallback, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------ batched search (tensor cores) */
 
 /* Leading dimension (in halves) of the fp16 tensor-core operand for `dim` features:

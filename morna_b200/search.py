@@ -133,7 +133,30 @@ class MornaSearch(object):
             self._ws = _lib.workspace(nbytes, self.device)
         return self._ws
 
-    def exact_search_device(self, queries, k, stream=None):
+    def single_search_device(self, query, k, stream=None):
+        """One query (CUDA float64 [dim]) through the HBM-bound FP32 scan + FP64 re-rank.
+        Same results as the FP64 scan; falls back to it when ties overflow the candidate list."""
+        assert query.is_cuda and query.dtype == torch.float64 and query.numel() == self.dim
+        query = query.contiguous()
+        n, dev = self.row_hi - self.row_lo, self.device
+        out_ids = torch.empty((1, k), dtype=torch.int32, device=dev)
+        out_d = torch.empty((1, k), dtype=torch.float64, device=dev)
+        if n == 0 or k > 512:
+            return self.exact_search_device(query.view(1, -1), k, stream, allow_single=False)
+        with torch.cuda.device(dev):
+            need = self.lib.morna_knn_single_workspace_bytes(n)
+            if getattr(self, "_sws", None) is None or self._sws.numel() < need:
+                self._sws = _lib.workspace(need, dev)
+                self._sfallback = torch.zeros(1, dtype=torch.int32, device=dev)
+            _lib.check(self.lib.morna_knn_single(
+                _lib.dev_ptr(self.vectors), _lib.dev_ptr(self.pp), n, self.dim, self.ld, self.row_lo,
+                _lib.ptr(query), k, _lib.dev_ptr(out_ids), _lib.dev_ptr(out_d), _lib.dev_ptr(self._sfallback),
+                _lib.dev_ptr(self._sws), self._sws.numel(), _lib.stream_ptr(stream)), "morna_knn_single")
+            if int(self._sfallback.item()):
+                return self.exact_search_device(query.view(1, -1), k, stream, allow_single=False)
+        return out_ids, out_d
+
+    def exact_search_device(self, queries, k, stream=None, allow_single=True):
         """queries: CUDA float64 [nq x dim] (row stride = queries.stride(0)).  Returns
         device (ids int32 [nq x k], dists float64 [nq x k]); ids are global internal
         ids (row_lo + local row); short lists are padded with id -1 / +inf."""
@@ -148,6 +171,8 @@ class MornaSearch(object):
         out_d = torch.full((nq, k), float("inf"), dtype=torch.float64, device=dev)
         if n == 0 or nq == 0:
             return out_ids, out_d
+        if nq == 1 and allow_single:
+            return self.single_search_device(queries[0], k, stream)
         with torch.cuda.device(dev):
             ws = self._workspace(self.lib.morna_knn_exact_workspace_bytes(n, nq, k))
             _lib.check(self.lib.morna_knn_exact(

@@ -319,3 +319,57 @@ def test_cli_index_then_exact_search_of_in_index_sample(tmp_path):
     check_topk(true_d, [int(r[1]) for r in got], [float(r[2]) for r in got], tol=1e-7, dist_tol=1e-5)
     with pytest.raises(ValueError):
         cli.main(["search", "-x", base, "-q", "999999", "-e"], stdout=io.StringIO())
+
+
+# ------------------------------------------------------------------ single query, FP32 scan + FP64 re-rank
+@pytest.mark.parametrize("n,d,k", [(21504, 3000, 100), (3000, 3000, 20), (5000, 130, 100), (900, 37, 64), (40, 16, 100)])
+def test_single_query_path_equals_fp64_scan(n, d, k):
+    _run_single_query_checks(n, d, k)
+
+
+def test_single_query_per_warp_load_variant():
+    from morna_b200 import _lib
+    lib = _lib.load()
+    try:
+        assert lib.morna_debug_set_tuning(3, 0) == 0
+        _run_single_query_checks(7000, 300, 100)
+    finally:
+        lib.morna_debug_set_tuning(3, 1)
+
+
+def _run_single_query_checks(n, d, k):
+    rng = np.random.default_rng(n + d + k)
+    S = rng.standard_normal((n, d)).astype(np.float32) * np.exp(rng.standard_normal((n, 1))).astype(np.float32)
+    S[n // 2] = 0.0
+    srch = make_search(S)
+    qs = [S[7].astype(np.float64), S[n - 1] + 0.03 * rng.standard_normal(d), rng.standard_normal(d) * 1e-3]
+    for qv in qs:
+        q = torch.from_numpy(qv).cuda()
+        s_ids, s_d = srch.single_search_device(q, k)
+        e_ids, e_d = srch.exact_search_device(q.view(1, -1), k, allow_single=False)
+        assert int(srch._sfallback.item()) == 0
+        assert torch.equal(s_ids, e_ids) and torch.equal(s_d, e_d)
+    true_d = c_oracle.distances(S, qs[-1])
+    m = min(k, n)
+    check_topk(true_d, s_ids[0].cpu().numpy()[:m], s_d[0].cpu().numpy()[:m], tol=1e-9)
+
+
+def test_single_query_ties_fall_back_and_shard_offsets():
+    oracle = mo.go_index(tiny_lines(), features=3000, sample_threshold=100)
+    S = oracle.matrix_f32()
+    srch = make_search(S)
+    q = torch.from_numpy(S[2040].astype(np.float64)).cuda()   # sample 1: one non-zero bucket
+    s_ids, s_d = srch.single_search_device(q, 20)
+    assert int(srch._sfallback.item()) == 1                  # 3737 rows tie at distance 0
+    e_ids, e_d = srch.exact_search_device(q.view(1, -1), 20, allow_single=False)
+    assert torch.equal(s_ids, e_ids) and torch.equal(s_d, e_d)
+    zero = torch.zeros(3000, dtype=torch.float64, device="cuda")
+    z_ids, z_d = srch.single_search_device(zero, 5)
+    assert z_ids[0].tolist() == [6849, 6848, 6847, 6846, 6845] and float(z_d[0, 0]) == math.sqrt(2.0)
+    rng = np.random.default_rng(3)
+    G = rng.standard_normal((1001, 64)).astype(np.float32)
+    full = make_search(G)
+    part = make_search(G, shard=(1, 2))
+    qg = torch.from_numpy(G[900].astype(np.float64)).cuda()
+    p_ids, p_d = part.single_search_device(qg, 10)
+    assert int(p_ids[0, 0]) == 900 and p_ids.min() >= 501
