@@ -39,11 +39,12 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+    """Samples SM clock, power and throttle reasons through NVML from before the warm-up on; `window()`
+    keeps the samples that fall inside the timed region."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+        self.index, self.rows, self.max_mhz, self.error, self._stop_evt = index, [], None, None, threading.Event()
 
     def run(self):
         try:
@@ -51,23 +52,25 @@ class ClockSampler(threading.Thread):
             nv.nvmlInit()
             h = nv.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
-                     "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80, "sync_boost": 0x10}
             while not self._stop_evt.is_set():
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                for name, bit in names.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-                time.sleep(0.05)
+                self.rows.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(h), nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
+                time.sleep(0.005)
         except Exception as exc:      # NVML absent: report that instead of clocks
-            self.reasons.add("nvml_unavailable:%s" % type(exc).__name__)
+            self.error = "nvml_unavailable:%s" % type(exc).__name__
 
-    def stop(self):
+    def window(self, t0, t1):
         self._stop_evt.set()
         self.join(timeout=2)
-        med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80, "sync_boost": 0x10}
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
+        reasons = sorted({n for r in rows for n, bit in names.items() if r[2] & bit})
+        if self.error:
+            reasons.append(self.error)
+        return {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(rows),
+                "power_w": float(np.mean([r[3] for r in rows])) if rows else None}
 
 
 def synth_matrix(torch, device, n, dim, seed):
@@ -92,6 +95,14 @@ def cpu_baseline_run(n_samples, dim, k, n_queries, threads, seed=1234):
     return n_queries / dt, dt
 
 
+def workload_config(n_samples, nq, world, rows_sharded):
+    return {"workload": "%d samples x %d features (gaussian, seed 1234), %d in-index queries per GPU per step, "
+                        "exact top-%d ids+distances" % (n_samples, DIM, nq, K),
+            "parallelism": ("rows-sharded x%d + NCCL all-gather merge" % world) if rows_sharded
+                           else ("replicated index, queries sharded x%d" % world),
+            "l2": "inputs larger than L2 (sample matrix %.0f MB)" % (n_samples * DIM * 4 / 1e6)}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU algorithm (C port of morna.py:681-712, the
     reference itself is Python 2 and cannot run here) on all host cores."""
@@ -110,10 +121,10 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "50000 samples x 3000 features, exact top-100, %d-query sample per step "
-                                   "(of the 4096-query batch)" % per_step},
+            "config": workload_config(N_SAMPLES, N_QUERIES, 1, False),
             "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
-                             "sample": "%d queries/step x %d steps, C port of exact_search_nn, one thread per core" % (per_step, args.steps)},
+                             "sample": "%d of the 4096 queries per step x %d steps, C port of exact_search_nn (morna.py:681-712; the "
+                                       "reference itself is Python 2 + annoy and cannot run here), one thread per core" % (per_step, args.steps)},
             "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -121,7 +132,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows-sharded", action="store_true", help="split rows across ranks + NCCL top-k merge")
@@ -164,7 +175,7 @@ def main():
         rows = torch.randperm(n_samples, generator=qg)[:nq].to(device)
         queries64 = S[rows].to(torch.float64)               # in-index queries (float32-valued)
     del S
-    host_q = queries64.cpu().pin_memory()
+    host_q = queries64.to(torch.float32).cpu().pin_memory()      # the queries are float32-valued rows
     host_ids = torch.empty((nq, K), dtype=torch.int32).pin_memory()
     host_d = torch.empty((nq, K), dtype=torch.float64).pin_memory()
 
@@ -178,7 +189,7 @@ def main():
         return ids, d
 
     def step_e2e():
-        q = host_q.to(device, non_blocking=True)
+        q = host_q.to(device, non_blocking=True).to(torch.float64)   # widened exactly on the device
         ids, d = srch.batched_search_device(q, K)
         if args.rows_sharded and world > 1:
             ids, d = mdist.all_gather_topk(ids, d)
@@ -192,6 +203,7 @@ def main():
             td.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank); sampler.start()
     for _ in range(args.warmup):
         ids, d = step_resident()
     torch.cuda.synchronize()
@@ -200,18 +212,19 @@ def main():
         assert float(d[:, 0].abs().max()) == 0.0
 
     # ---- timed region: K steps, inputs resident, CUDA events, max over ranks
-    sampler = ClockSampler(local_rank); sampler.start()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
         step_resident()
     ev1.record()
     barrier()
+    wall1 = time.perf_counter()
     ms_total = ev0.elapsed_time(ev1)
     launches = _lib.launch_count() - launches0
-    clocks = sampler.stop()
+    clocks = sampler.window(wall0, wall1)
     t = torch.tensor([ms_total], dtype=torch.float64, device=device)
     if world > 1:
         td.all_reduce(t, op=td.ReduceOp.MAX)
@@ -249,12 +262,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": roofline.pop("dtype"), "data": "synthetic",
-                "config": {"workload": "%d samples x %d features (gaussian, seed 1234), %d in-index queries per GPU "
-                                       "per step, exact top-%d ids+distances" % (n_samples, DIM, nq, K),
-                           "parallelism": ("rows-sharded x%d + NCCL all-gather merge" % world) if args.rows_sharded
-                                          else ("replicated index, queries sharded x%d" % world),
-                           "l2": "inputs larger than L2 (sample matrix %.0f MB)" % (n_samples * DIM * 4 / 1e6)},
-                "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(host_q.numel() * 8),
+                "config": workload_config(n_samples, nq, world, args.rows_sharded),
+                "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(host_q.numel() * host_q.element_size()),
                         "d2h_bytes_per_step": int(host_ids.numel() * 4 + host_d.numel() * 8)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "peaks": peaks["source"]}
@@ -286,8 +295,13 @@ def dominant_kernel_roofline(torch, lib, _lib, srch, queries64, peaks):
     flops = 2.0 * nq * rows * srch.dim
     achieved = flops / (ms / 1e3) / 1e12
     peak = peaks["bf16_tflops"]
-    return {"bound": "tensor", "kernel": "knn_gemm_kernel (tcgen05 fp16 UMMA, filter pass over %d rows)" % rows,
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "r01_step_summary.json")     # dram bytes per launch from the committed ncu capture
+    if os.path.exists(prof):
+        with open(prof) as fh:
+            traffic = json.load(fh).get("knn_gemm2_filter_dram_bytes")
+    return {"bound": "tensor", "kernel": "knn_gemm2_kernel<4> (tcgen05 cta_group::2 fp16 UMMA, filter pass over %d rows)" % rows,
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
             "algorithmic": "2*Q*N*D flops per launch, Q=%d N=%d D=%d" % (nq, rows, srch.dim),
             "launch_ms": ms, "peak_source": peaks["source"] + " bf16 burst (fp16 runs on the same kind::f16 pipe)",
             "phase_ms": {name: round(v, 4) for name, v in zip(PHASE_NAMES, acc)},

@@ -249,12 +249,20 @@ class MornaSearch(object):
             return parts[0]
         return mdist.merge_topk(torch.cat([p[0] for p in parts], 1), torch.cat([p[1] for p in parts], 1), k, stream)
 
-    def exact_search_batch(self, queries, k):
-        """Host entry: queries numpy [nq x dim] (float32 or float64) -> numpy (ids, dists)."""
-        q = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float64))
+    def exact_search_batch(self, queries, k, tensor_cores=None):
+        """Host entry: queries numpy [nq x dim] (float32 or float64) -> numpy (ids, dists).
+        float32 queries cross PCIe as float32 and are widened (exactly) on the device.  Batches of 64+
+        queries use the tensor-core path, which returns the same bits as the scan."""
+        queries = np.ascontiguousarray(queries)
+        if queries.dtype != np.float32:
+            queries = queries.astype(np.float64, copy=False)
+        q = torch.from_numpy(queries)
         if q.numel():
             q = q.pin_memory()
-        ids, d = self.exact_search_device(q.to(self.device, non_blocking=True), k)
+        qd = q.to(self.device, non_blocking=True).to(torch.float64)
+        if tensor_cores is None:
+            tensor_cores = qd.shape[0] >= 64
+        ids, d = (self.batched_search_device if tensor_cores else self.exact_search_device)(qd, k)
         return ids.cpu().numpy(), d.cpu().numpy()
 
     def exact_search_nn(self, num_neighbors, include_distances=True, meta_db=False):
