@@ -3,6 +3,7 @@
 #include <math.h>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
 
@@ -71,7 +72,44 @@ first_position_kernel(const int64_t *__restrict__ row_off, const uint8_t *__rest
         const int64_t b = row_off[j], e = row_off[j + 1];
         for (int64_t p = b + lane; p < e; p += 32) {
             int32_t s = sample[p];
-            if ((uint32_t)s <= (uint32_t)max_sample_id) atomicMin(&first_pos[s], (unsigned long long)p);
+            // positions only ever decrease: a plain (possibly stale) read filters nearly every atomic
+            if ((uint32_t)s <= (uint32_t)max_sample_id && (unsigned long long)p < __ldcg(&first_pos[s]))
+                atomicMin(&first_pos[s], (unsigned long long)p);
+        }
+    }
+}
+
+// Same result with a CTA-local table in shared memory (sample ids <= kFirstPosSmemIds, nnz < 2^32):
+// a pair only reaches the global atomic when it lowers this CTA's own minimum for the sample.
+constexpr int kFirstPosSmemIds = 49152;      // 192 KB of uint32
+
+__global__ void __launch_bounds__(512)
+first_position_smem_kernel(const int64_t *__restrict__ row_off, const uint8_t *__restrict__ pass, int64_t n_rows,
+                           const int32_t *__restrict__ sample, int32_t max_sample_id,
+                           unsigned long long *__restrict__ first_pos) {
+    extern __shared__ uint32_t s_first[];            // [max_sample_id + 1]
+    for (int i = threadIdx.x; i <= max_sample_id; i += blockDim.x) s_first[i] = 0xffffffffu;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n_rows; j += warps_total) {
+        if (!pass[j]) continue;
+        const int64_t b = row_off[j], e = row_off[j + 1];
+        for (int64_t p0 = b; p0 < e; p0 += 256) {          // eight independent loads in flight per lane
+            int32_t sv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int64_t p = p0 + u * 32 + lane;
+                sv[u] = p < e ? __ldg(sample + p) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int64_t p = p0 + u * 32 + lane;
+                if ((uint32_t)sv[u] <= (uint32_t)max_sample_id) {
+                    const uint32_t old = atomicMin(&s_first[sv[u]], (uint32_t)p);
+                    if ((uint32_t)p < old) atomicMin(&first_pos[sv[u]], (unsigned long long)p);
+                }
+            }
         }
     }
 }
@@ -150,6 +188,151 @@ index_accumulate_kernel(const int64_t *__restrict__ row_off, const int8_t *__res
     for (int i = threadIdx.x; i < width; i += kAccThreads) out[i] = col[i];
 }
 
+// ---- pipelined variant -------------------------------------------------------------------------
+// Same order-faithful accumulation, but the bucket's pairs are treated as one virtual stream
+// (rows of the bucket concatenated in file order) cut into batches of kAcc2Threads*kAcc2U pairs.
+// Three batches are in flight per CTA: sample/coverage loads for batch i+2, the id_of_sample gather
+// for batch i+1, and the ordered shared-memory adds of batch i (a barrier between rows), so the two
+// dependent global-memory latencies are hidden instead of being paid once per row.
+constexpr int kAcc2Threads = 512, kAcc2U = 4, kAcc2Batch = kAcc2Threads * kAcc2U;
+constexpr int kAcc2Window = 512;          // rows of the bucket whose metadata sits in shared memory
+constexpr int kAcc2Tile = 22528;          // doubles of the bucket column per CTA (176 KB)
+constexpr size_t kAcc2MetaBytes = (size_t)kAcc2Window * (8 + 8) + (size_t)(kAcc2Window + 1) * 4 + 16;
+
+__global__ void __launch_bounds__(256)
+sorted_row_len_kernel(const int64_t *__restrict__ row_off, const int32_t *__restrict__ rows_by_bucket, int64_t n_rows,
+                      int64_t *__restrict__ len) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t j = rows_by_bucket[i];
+        len[i] = row_off[j + 1] - row_off[j];
+    }
+}
+
+// rows whose sample ids are strictly increasing or strictly decreasing cannot list a sample twice
+__global__ void __launch_bounds__(256)
+rows_monotonic_kernel(const int64_t *__restrict__ row_off, const uint8_t *__restrict__ pass, int64_t n_rows,
+                      const int32_t *__restrict__ sample, int32_t *__restrict__ not_monotonic) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n_rows; j += warps_total) {
+        if (!pass[j]) continue;
+        const int64_t b = row_off[j], e = row_off[j + 1];
+        bool up = true, down = true;
+        for (int64_t p = b + 1 + lane; p < e; p += 32) {
+            const int32_t a = sample[p - 1], c = sample[p];
+            up &= c > a; down &= c < a;
+        }
+        up = __all_sync(kFull, up); down = __all_sync(kFull, down);
+        if (lane == 0 && !up && !down) *not_monotonic = 1;
+    }
+}
+
+template <bool kAtomic>
+__global__ void __launch_bounds__(kAcc2Threads)
+index_accumulate2_kernel(const int32_t *__restrict__ run_flag, const int64_t *__restrict__ row_off, const int8_t *__restrict__ sign,
+                         const double *__restrict__ idf, const int32_t *__restrict__ sample,
+                         const int32_t *__restrict__ cov, const int32_t *__restrict__ id_of_sample,
+                         const int32_t *__restrict__ rows_by_bucket, const int32_t *__restrict__ bucket_begin,
+                         const int64_t *__restrict__ voff, int32_t id_lo, int32_t id_hi, int32_t tile,
+                         double *__restrict__ acc, int64_t acc_ld) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *col = reinterpret_cast<double *>(smem_raw);                       // [tile]
+    double *s_w = col + tile;                                                 // [window] sign * idf
+    int64_t *s_delta = reinterpret_cast<int64_t *>(s_w + kAcc2Window);        // [window] real offset - virtual offset
+    int32_t *s_voff = reinterpret_cast<int32_t *>(s_delta + kAcc2Window);     // [window + 1] virtual offsets - V0
+    __shared__ int s_rows[8];                                                 // first/last row of the 4 batches in flight
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x;
+    const int32_t lo = id_lo + (int32_t)blockIdx.y * tile;
+    const int32_t hi = min(id_hi, lo + tile);
+    const int32_t width = hi - lo;
+    const int32_t r_begin = bucket_begin[b], r_end = bucket_begin[b + 1];
+    double *out = acc + (int64_t)b * acc_ld + (lo - id_lo);
+    // the atomic and the plain variant are both launched; the monotonicity flag picks the one that runs
+    if ((*run_flag != 0) != kAtomic) return;
+    if (r_begin == r_end) return;            // acc was zero-filled by the caller
+    for (int i = tid; i < width; i += kAcc2Threads) col[i] = 0.0;
+
+    for (int32_t w0 = r_begin; w0 < r_end; w0 += kAcc2Window) {
+        const int nrows = min(kAcc2Window, r_end - w0);
+        const int64_t V0 = voff[w0], V1 = voff[w0 + nrows];
+        __syncthreads();                     // previous window fully applied; metadata may be replaced
+        for (int i = tid; i <= nrows; i += kAcc2Threads) s_voff[i] = (int32_t)(voff[w0 + i] - V0);
+        for (int i = tid; i < nrows; i += kAcc2Threads) {
+            const int32_t j = rows_by_bucket[w0 + i];
+            s_w[i] = (double)sign[j] * idf[j];            // +-idf: (+-idf)*cov == +-(idf*cov) bit for bit
+            s_delta[i] = row_off[j] - voff[w0 + i];
+        }
+        __syncthreads();
+        const int64_t total = V1 - V0;
+        const int n_batches = (int)((total + kAcc2Batch - 1) / kAcc2Batch);
+
+        // register stages: L = loaded (sample, cov, row), G = gathered (id, value, row)
+        int32_t l_s[kAcc2U], l_c[kAcc2U], l_r[kAcc2U];
+        int32_t g_id[kAcc2U], g_r[kAcc2U];
+        double g_v[kAcc2U];
+        auto load_batch = [&](int bi) {
+            // one binary search for the thread's first pair, then a forward walk: its next pairs are
+            // kAcc2Threads further along the stream, usually in the same or the next row
+            int a = 0;
+            const int64_t v_first = (int64_t)bi * kAcc2Batch + tid;
+            if (bi < n_batches && v_first < total) {
+                int z = nrows;
+                while (z - a > 1) { const int m = (a + z) >> 1; if (s_voff[m] <= (int32_t)v_first) a = m; else z = m; }
+            }
+            const int64_t v_last = min(total, (int64_t)(bi + 1) * kAcc2Batch) - 1;      // last pair of the batch
+#pragma unroll
+            for (int u = 0; u < kAcc2U; ++u) {
+                const int64_t v = v_first + u * kAcc2Threads;                            // relative to V0
+                l_r[u] = -1;
+                if (bi < n_batches && v < total) {
+                    while (a + 1 < nrows && s_voff[a + 1] <= (int32_t)v) ++a;
+                    const int64_t p = V0 + v + s_delta[a];
+                    l_s[u] = __ldg(sample + p); l_c[u] = __ldg(cov + p); l_r[u] = a;
+                    if (v == (int64_t)bi * kAcc2Batch) s_rows[(bi & 3) * 2] = a;         // first row of the batch
+                    if (v == v_last) s_rows[(bi & 3) * 2 + 1] = a;                       // last row of the batch
+                }
+            }
+        };
+        auto gather_batch = [&]() {
+#pragma unroll
+            for (int u = 0; u < kAcc2U; ++u) {
+                g_r[u] = l_r[u];
+                if (l_r[u] >= 0) {
+                    g_id[u] = __ldg(id_of_sample + l_s[u]);
+                    g_v[u] = (double)l_c[u] * s_w[l_r[u]];
+                }
+            }
+        };
+        load_batch(0);
+        gather_batch();                      // batch 0 gathered
+        load_batch(1);
+        __syncthreads();                     // s_rows of batches 0 and 1 visible
+        for (int bi = 0; bi < n_batches; ++bi) {
+            // keep a copy of the batch to apply, then advance the two younger stages
+            int32_t a_id[kAcc2U], a_r[kAcc2U];
+            double a_v[kAcc2U];
+#pragma unroll
+            for (int u = 0; u < kAcc2U; ++u) { a_id[u] = g_id[u]; a_r[u] = g_r[u]; a_v[u] = g_v[u]; }
+            gather_batch();                  // batch bi+1: its id gather flies during the adds below
+            load_batch(bi + 2);
+            // rows covered by batch bi (recorded when it was loaded, at least one barrier ago), in file order
+            const int ra = s_rows[(bi & 3) * 2], rb = s_rows[(bi & 3) * 2 + 1];
+            for (int r = ra; r <= rb; ++r) {
+#pragma unroll
+                for (int u = 0; u < kAcc2U; ++u)
+                    if (a_r[u] == r && a_id[u] >= lo && a_id[u] < hi) {
+                        if (kAtomic) atomicAdd(&col[a_id[u] - lo], a_v[u]);     // a row may repeat a sample
+                        else col[a_id[u] - lo] += a_v[u];                        // distinct ids within the row
+                    }
+                __syncthreads();
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < width; i += kAcc2Threads) out[i] = col[i];
+}
+
 // ------------------------------------------------------------------ round + transpose
 __global__ void __launch_bounds__(256)
 round_store_kernel(const double *__restrict__ acc, int64_t acc_ld, int32_t n_ids, int32_t dim,
@@ -190,7 +373,7 @@ static IdsWs ids_ws_layout(int64_t m) {
     return w;
 }
 
-struct AccWs { size_t keys_in, keys_out, vals_in, vals_out, begin, cub, cub_bytes, total; };
+struct AccWs { size_t keys_in, keys_out, vals_in, vals_out, begin, cub, cub_bytes, len, voff, scan, scan_bytes, flag, total; };
 static AccWs acc_ws_layout(int64_t n_rows, int32_t dim) {
     AccWs w{};
     size_t off = 0;
@@ -203,9 +386,18 @@ static AccWs acc_ws_layout(int64_t n_rows, int32_t dim) {
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const int32_t *)nullptr, (int32_t *)nullptr,
                                     (const int32_t *)nullptr, (int32_t *)nullptr, (int)n_rows, 0, 32);
     w.cub = off; w.cub_bytes = cub_bytes; off += align_up(cub_bytes, 256);
+    w.len = off; off += align_up((size_t)(n_rows + 1) * 8, 256);
+    w.voff = off; off += align_up((size_t)(n_rows + 1) * 8, 256);
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int64_t *)nullptr, (int64_t *)nullptr, (int)(n_rows + 1));
+    w.scan = off; w.scan_bytes = scan_bytes; off += align_up(scan_bytes, 256);
+    w.flag = off; off += 256;
     w.total = off + 256;
     return w;
 }
+
+static int g_acc_pipelined = 1;      // morna_debug_set_tuning key 4
+void set_acc_pipelined(int v) { g_acc_pipelined = v ? 1 : 0; }
 
 static unsigned grid_for(int64_t work, int threads) {
     int64_t g = (work + threads - 1) / threads;
@@ -267,8 +459,22 @@ extern "C" int morna_assign_internal_ids(const int64_t *row_off, const uint8_t *
     ids_init_kernel<<<grid_for(m, 256), 256, 0, s>>>(first_pos, vals_in, m, sentinel);
     MORNA_LAUNCH_CHECK();
     if (n_rows > 0 && nnz > 0) {
-        first_position_kernel<<<grid_for(n_rows * 32, 256), 256, 0, s>>>(row_off, pass, n_rows, sample,
-                                                                        max_sample_id, first_pos);
+        if (m <= kFirstPosSmemIds && nnz < 0xffffffffLL) {
+            const size_t smem = (size_t)m * sizeof(uint32_t);
+            if (smem > 48 * 1024)
+                MORNA_CUDA_TRY(cudaFuncSetAttribute(first_position_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)(kFirstPosSmemIds * sizeof(uint32_t))));
+            int per_sm = (int)((220 * 1024) / (smem + 1024));
+            if (per_sm > 4) per_sm = 4;
+            if (per_sm < 1) per_sm = 1;
+            int64_t blocks = (n_rows + 15) / 16;
+            if (blocks > 148LL * per_sm) blocks = 148LL * per_sm;
+            first_position_smem_kernel<<<(unsigned)blocks, 512, smem, s>>>(row_off, pass, n_rows, sample, max_sample_id,
+                                                                         first_pos);
+        } else {
+            first_position_kernel<<<grid_for(n_rows * 32, 256), 256, 0, s>>>(row_off, pass, n_rows, sample,
+                                                                            max_sample_id, first_pos);
+        }
         MORNA_LAUNCH_CHECK();
     }
     size_t cub_bytes = w.cub_bytes;
@@ -316,6 +522,37 @@ extern "C" int morna_index_accumulate(const int64_t *row_off, const uint8_t *pas
     bucket_begin_kernel<<<grid_for(n_rows + 1, 256), 256, 0, s>>>(keys_out, n_rows, dim, begin);
     MORNA_LAUNCH_CHECK();
     const int32_t range = id_hi - id_lo;
+    if (g_acc_pipelined) {
+        auto *len = (int64_t *)(ws + w.len);
+        auto *voff = (int64_t *)(ws + w.voff);
+        MORNA_CUDA_TRY(cudaMemsetAsync(len + n_rows, 0, sizeof(int64_t), s));
+        sorted_row_len_kernel<<<grid_for(n_rows, 256), 256, 0, s>>>(row_off, vals_out, n_rows, len);
+        MORNA_LAUNCH_CHECK();
+        size_t scan_bytes = w.scan_bytes;
+        MORNA_CUDA_TRY(cub::DeviceScan::ExclusiveSum(ws + w.scan, scan_bytes, len, voff, (int)(n_rows + 1), s));
+        count_launch(2);
+        const int32_t tile2 = range < kAcc2Tile ? range : kAcc2Tile;
+        const int32_t tiles2 = (range + tile2 - 1) / tile2;
+        const size_t smem2 = (size_t)tile2 * sizeof(double) + kAcc2MetaBytes;
+        auto *flag = (int32_t *)(ws + w.flag);
+        MORNA_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int32_t), s));
+        rows_monotonic_kernel<<<grid_for(n_rows * 32, 256), 256, 0, s>>>(row_off, pass, n_rows, sample, flag);
+        MORNA_LAUNCH_CHECK();
+        if (smem2 > 48 * 1024) {
+            MORNA_CUDA_TRY(cudaFuncSetAttribute(index_accumulate2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(kAcc2Tile * sizeof(double) + kAcc2MetaBytes)));
+            MORNA_CUDA_TRY(cudaFuncSetAttribute(index_accumulate2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(kAcc2Tile * sizeof(double) + kAcc2MetaBytes)));
+        }
+        dim3 grid2((unsigned)dim, (unsigned)tiles2);
+        index_accumulate2_kernel<false><<<grid2, kAcc2Threads, smem2, s>>>(flag, row_off, sign, idf, sample, cov, id_of_sample,
+                                                                         vals_out, begin, voff, id_lo, id_hi, tile2, acc, acc_ld);
+        MORNA_LAUNCH_CHECK();
+        index_accumulate2_kernel<true><<<grid2, kAcc2Threads, smem2, s>>>(flag, row_off, sign, idf, sample, cov, id_of_sample,
+                                                                        vals_out, begin, voff, id_lo, id_hi, tile2, acc, acc_ld);
+        MORNA_LAUNCH_CHECK();
+        return MORNA_OK;
+    }
     const int32_t tile = range < kAccTile ? range : kAccTile;
     const int32_t tiles = (range + tile - 1) / tile;
     const size_t smem = (size_t)tile * sizeof(double);

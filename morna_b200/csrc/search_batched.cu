@@ -974,11 +974,12 @@ extern "C" int morna_debug_tensor_scores(const void *hs, int64_t ld_h, const flo
 
 /* Experiment knobs, process-wide: key 0 = GEMM variant (1 CTA pairs / 0 single CTA),
  * key 1 = shared-memory pipeline stages of the pair variant (4 or 6). */
-namespace morna { void set_single_tma(int v); }
+namespace morna { void set_single_tma(int v); void set_acc_pipelined(int v); }
 
 extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
     if (key == 0) g_gemm_pair = value ? 1 : 0;
     else if (key == 3) morna::set_single_tma(value);
+    else if (key == 4) morna::set_acc_pipelined(value);
     else if (key == 1) g_gemm_stages = value;
 
     else return MORNA_ERR_INVALID_ARGUMENT;

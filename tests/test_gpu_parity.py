@@ -128,6 +128,23 @@ def test_index_build_synthetic_bit_exact(features, threshold, n_samples):
         assert float(idx.vectors[:, idx.dim:].abs().max()) == 0.0
 
 
+def test_index_build_rows_with_repeated_or_unsorted_samples():
+    """A row that is not monotonic (or lists a sample twice) takes the atomic variant of the scatter-add."""
+    from morna_b200.index import MornaIndex
+    rng = np.random.default_rng(33)
+    lines = synthetic_rows(rng, 120, 400)
+    lines.insert(5, "chr9\t5\t9\t+\tGT\tAG\t7,3,9,3,250,1\t2,4,1,8,5,1\n")       # sample 3 twice, unsorted
+    lines.append("chr9\t50\t90\t+\tGT\tAG\t5,9,2,77\t1,1,1,1\n")                  # unsorted, distinct
+    oracle = mo.go_index(lines, features=50, sample_threshold=2)
+    idx = MornaIndex(oracle.sample_count, "unused", dim=50, sample_threshold=2)
+    idx.add_lines(lines)
+    idx.build()
+    assert idx.internal_id_map == oracle.internal_id_map
+    got, want = idx.accumulator_f64(), oracle.matrix_f64()
+    np.testing.assert_allclose(got, want, rtol=1e-15, atol=0)      # repeated sample: last-ulp order freedom only
+    assert np.array_equal(idx.matrix_f32(), oracle.matrix_f32())
+
+
 def test_index_build_id_range_shards_concatenate():
     from morna_b200.index import MornaIndex
     rng = np.random.default_rng(21)
