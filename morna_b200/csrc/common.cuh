@@ -55,6 +55,19 @@ __device__ __forceinline__ double warp_sum(double v) {
 // exactly 0 from itself (morna.py:101-114 has the same property sequentially).
 struct Dot3 { double pp, pq; };
 
+// float -> double without the conversion unit (F2F.F64.F32 issues at a quarter of the DFMA rate and
+// was the re-rank's busiest pipe): the float's sign/exponent/mantissa bits dropped into a double
+// *without re-biasing the exponent*, i.e. exactly v * 2^-896 -- zeros and denormals included, three
+// integer instructions.  The other FMA operand carries the 2^896 (kTwo896), so
+//   fma(f32_scaled_f64(v), q * 2^896, acc) == fma((double)v, q, acc)   bit for bit
+// whenever q * 2^896 is finite (|q| < 2^128).  Inf/NaN inputs are not supported on this path.
+constexpr double kTwo896 = 0x1p896;
+constexpr double kScaledQueryMax = 0x1p127;
+__device__ __forceinline__ double f32_scaled_f64(float v) {
+    const int b = __float_as_int(v);
+    return __hiloint2double((b >> 3) & (int)0x8fffffff, b << 29);
+}
+
 // angular distance from the three sums; morna.py:109-114 plus a clamp at 0
 __device__ __forceinline__ double angular_from_sums(double pp, double qq, double pq) {
     double ppqq = pp * qq;

@@ -12,6 +12,7 @@
 //      under the reference order, so ids and distances equal morna_knn_exact bit for bit.
 // Replaces the N x D Python loop of exact_search_nn (morna.py:697-712) for query batches.
 #include <cuda_fp16.h>
+#include <limits.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -62,7 +63,8 @@ prep_samples_kernel(const float *__restrict__ vectors, const double *__restrict_
 __global__ void __launch_bounds__(kPrepThreads)
 prep_queries_kernel(const double *__restrict__ queries, int64_t nq, int64_t nq_pad, int32_t dim, int64_t q_ld,
                     __half *__restrict__ hq, int64_t ld_h, double *__restrict__ qq_out, float *__restrict__ eps_out,
-                    const float *__restrict__ rho_max, float eps_acc) {
+                    const float *__restrict__ rho_max, float eps_acc, uint8_t *__restrict__ overflow,
+                    int32_t *__restrict__ stats) {
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = (int64_t)gridDim.x * (kPrepThreads / 32);
     const int chunks_h = (int)(ld_h >> 2);
@@ -74,14 +76,20 @@ prep_queries_kernel(const double *__restrict__ queries, int64_t nq, int64_t nq_p
         }
         const double *q = queries + row * q_ld;
         double acc = 0.0;
+        bool huge = false;                               // the re-rank stages q * 2^896 (f32_scaled_f64)
         for (int c = lane; 4 * c < dim; c += 32) {       // same lane/chunk partition as the scan
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 double a = (4 * c + t < dim) ? q[4 * c + t] : 0.0;
+                huge |= !(fabs(a) < kScaledQueryMax);
                 acc = fma(a, a, acc);
             }
         }
         acc = warp_sum(acc);
+        if (__any_sync(kFull, huge) && overflow && lane == 0) {      // left to the exact scan
+            overflow[row] = 1;
+            atomicAdd(stats + 0, 1);
+        }
         const double norm = sqrt(acc);
         const double inv = norm > 0.0 ? 1.0 / norm : 0.0;
         double res = 0.0;
@@ -495,7 +503,7 @@ kth_warp_kernel(KthParams p, int nq) {
     else {
         count = p.cand_cnt[q];
         if (count > p.cap) {            // survivors were dropped: the exact scan must answer this query
-            if (lane == 0) { p.overflow[q] = 1; atomicAdd(p.stats + 0, 1); p.fin_cnt[q] = 0; }
+            if (lane == 0) { if (!p.overflow[q]) atomicAdd(p.stats + 0, 1); p.overflow[q] = 1; p.fin_cnt[q] = 0; }
             return;
         }
     }
@@ -590,7 +598,7 @@ kth_warp_kernel(KthParams p, int nq) {
             p.cand_cnt[q] = out;                     // the filter pass appends after these
         } else {
             int kept = out;
-            if (kept > p.fcap) { p.overflow[q] = 1; atomicAdd(p.stats + 0, 1); kept = 0; }
+            if (kept > p.fcap) { if (!p.overflow[q]) atomicAdd(p.stats + 0, 1); p.overflow[q] = 1; kept = 0; }
             p.fin_cnt[q] = kept;
             atomicAdd(p.stats + 1, count);
             atomicAdd(p.stats + 2, kept);
@@ -600,89 +608,187 @@ kth_warp_kernel(KthParams p, int nq) {
 }
 
 // ------------------------------------------------------------------ exact re-rank + final order
-constexpr int kRerankThreads = 512;
+constexpr int kRrThreads = 128;                // 4 warps per CTA, several CTAs per SM
+constexpr int kOrderThreads = 128;
 
-// Persistent CTAs (two per SM), each loops over queries: FP64 distances of the query's candidates
-// with the canonical sums (one warp per candidate row, four 16-byte loads in flight per lane), then
-// a bitonic sort under the reference order and the first k written out.  HBM-gather bound:
-// candidates * 4 * ld bytes per query.  Small enough (40 KB smem, 40 registers) to share an SM with
-// the GEMM CTA of the next query chunk.
-__global__ void __launch_bounds__(kRerankThreads)
-rerank_select_kernel(const float *__restrict__ vectors, const double *__restrict__ pp, int64_t ld, int32_t dim,
-                     int32_t id_base, const double *__restrict__ queries, int64_t q_ld,
-                     const double *__restrict__ qq, const int32_t *__restrict__ fin_id,
-                     const int32_t *__restrict__ fin_cnt, const uint8_t *__restrict__ overflow, int32_t fcap,
-                     int32_t k, int32_t nq, int32_t *__restrict__ out_ids, double *__restrict__ out_dist) {
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double2 ldg_f64x2_hint(const double *p, uint64_t pol) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+                 : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
+    return r;
+}
+
+struct RerankParams {
+    const float *vectors; const double *pp; int64_t ld; int32_t dim, id_base, n;
+    const double *queries; int64_t q_ld; const double *qq;
+    const int32_t *fin_id; const int32_t *fin_cnt; const uint8_t *overflow;
+    int32_t fcap, nq, phases, phase_rows;
+    double *fin_dist;
+};
+
+// Exact FP64 distances of every (query, candidate row) pair.  A work item is (query, row phase):
+// the CTA stages the query once in shared memory (pre-multiplied by 2^896, see f32_scaled_f64),
+// compacts the candidates whose rows fall in the phase's row range, and each warp then takes kRows
+// candidate rows at a time so that one shared-memory read of a query chunk feeds kRows FMAs -- the
+// load/store unit, not HBM, limited the one-row-per-warp version.  Per row the sum is the canonical
+// one (lane l owns float4 chunks l, l+32, ...; one accumulator; fixed butterfly), so the distances
+// equal the exact scan's bit for bit.  Items are walked phase-major: with few rows and many queries
+// (rows re-ranked several times per batch) the row range of a phase stays L2-resident while all
+// queries pass over it; phases == 1 is the plain query-major gather.
+template <int kRows>
+__global__ void __launch_bounds__(kRrThreads)
+rerank_dist_kernel(const RerankParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *qs = reinterpret_cast<double *>(smem_raw);                 // [ld]
-    double *sd = qs + ld;                                              // [fcap]
-    int *si = reinterpret_cast<int *>(sd + fcap);                      // [fcap]
+    double *qs = reinterpret_cast<double *>(smem_raw);                   // [ld]  query * 2^896
+    int *list = reinterpret_cast<int *>(qs + p.ld);                      // [fcap] positions in the candidate list
+    __shared__ int s_count;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int chunks = (int)(ld >> 2);
-    for (int q = blockIdx.x; q < nq; q += gridDim.x) {
-        int32_t *oi = out_ids + (int64_t)q * k;
-        double *od = out_dist + (int64_t)q * k;
-        if (overflow[q]) {               // answered by the exact scan afterwards
-            for (int i = tid; i < k; i += kRerankThreads) { oi[i] = -1; od[i] = INFINITY; }
-            continue;
+    const int chunks = (int)(p.ld >> 2);
+    const uint64_t pol = l2_policy_evict_first();
+    const int64_t total = (int64_t)p.nq * p.phases;
+    for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+        const int ph = (int)(t / p.nq), q = (int)(t - (int64_t)ph * p.nq);
+        if (p.overflow[q]) continue;                                     // answered by the exact scan afterwards
+        const int count = min(p.fin_cnt[q], p.fcap);
+        const int32_t *ids = p.fin_id + (int64_t)q * p.fcap;
+        const int lo = p.id_base + ph * p.phase_rows;
+        const int hi = ph == p.phases - 1 ? INT_MAX : lo + p.phase_rows;
+        __syncthreads();                                                 // previous item is done with qs/list
+        if (warp == 0) {
+            int m = 0;
+            for (int i0 = 0; i0 < count; i0 += 32) {
+                const int i = i0 + lane;
+                const int id = i < count ? ids[i] : -1;
+                const bool keep = i < count && id >= lo && id < hi;
+                const unsigned mask = __ballot_sync(kFull, keep);
+                if (keep) list[m + __popc(mask & ((1u << lane) - 1u))] = i;
+                m += __popc(mask);
+            }
+            if (lane == 0) s_count = m;
         }
-        const int count = min(fin_cnt[q], fcap);
-        __syncthreads();                 // previous query's sort buffers are free
-        for (int c = tid; c < ld; c += kRerankThreads) qs[c] = c < dim ? queries[(int64_t)q * q_ld + c] : 0.0;
-        int P = 32;
-        while (P < count) P <<= 1;
-        for (int i = tid; i < P; i += kRerankThreads) { sd[i] = INFINITY; si[i] = -1; }
         __syncthreads();
-        const double qqv = qq[q];
-        for (int i = warp; i < count; i += kRerankThreads / 32) {
-            const int id = fin_id[(int64_t)q * fcap + i];
-            const int64_t row = id - id_base;
-            const float4 *src = reinterpret_cast<const float4 *>(vectors + row * ld);
-            double acc = 0.0;
+        const int m = s_count;
+        if (m == 0) continue;
+        {
+            const double *qsrc = p.queries + (int64_t)q * p.q_ld;
+            if ((p.q_ld & 1) == 0 && (p.dim & 1) == 0) {
+                for (int c = 2 * tid; c < (int)p.ld; c += 2 * kRrThreads) {
+                    double2 v = make_double2(0.0, 0.0);
+                    if (c < p.dim) v = ldg_f64x2_hint(qsrc + c, pol);
+                    qs[c] = v.x * kTwo896; qs[c + 1] = v.y * kTwo896;
+                }
+            } else {
+                for (int c = tid; c < (int)p.ld; c += kRrThreads) qs[c] = c < p.dim ? qsrc[c] * kTwo896 : 0.0;
+            }
+        }
+        __syncthreads();
+        const double qqv = p.qq[q];
+        for (int g = warp * kRows; g < m; g += (kRrThreads / 32) * kRows) {
+            const float4 *src[kRows];
+            int pos[kRows];
+            int64_t row[kRows];
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) {
+                pos[u] = list[min(g + u, m - 1)];                        // the tail repeats the last row
+                row[u] = (int64_t)ids[pos[u]] - p.id_base;
+                src[u] = reinterpret_cast<const float4 *>(p.vectors + row[u] * p.ld);
+            }
+            double acc[kRows];
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) acc[u] = 0.0;
             int c = lane;
-            for (; c + 96 < chunks; c += 128) {
-                float4 v[4];
+            for (; c + 32 < chunks; c += 64) {
+                float4 v[2][kRows];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = ldg_stream_f4(src + c + 32 * u);
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const double *qp = qs + 4 * (c + 32 * u);
-                    double2 qa = *reinterpret_cast<const double2 *>(qp);
-                    double2 qb = *reinterpret_cast<const double2 *>(qp + 2);
-                    acc = fma((double)v[u].x, qa.x, acc); acc = fma((double)v[u].y, qa.y, acc);
-                    acc = fma((double)v[u].z, qb.x, acc); acc = fma((double)v[u].w, qb.y, acc);
+                    for (int u = 0; u < kRows; ++u) v[h][u] = ldg_stream_f4(src[u] + c + 32 * h);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const double2 qa = *reinterpret_cast<const double2 *>(qs + 4 * (c + 32 * h));
+                    const double2 qb = *reinterpret_cast<const double2 *>(qs + 4 * (c + 32 * h) + 2);
+#pragma unroll
+                    for (int u = 0; u < kRows; ++u) {
+                        acc[u] = fma(f32_scaled_f64(v[h][u].x), qa.x, acc[u]);
+                        acc[u] = fma(f32_scaled_f64(v[h][u].y), qa.y, acc[u]);
+                        acc[u] = fma(f32_scaled_f64(v[h][u].z), qb.x, acc[u]);
+                        acc[u] = fma(f32_scaled_f64(v[h][u].w), qb.y, acc[u]);
+                    }
                 }
             }
             for (; c < chunks; c += 32) {
-                float4 v = ldg_stream_f4(src + c);
-                double2 qa = *reinterpret_cast<const double2 *>(qs + 4 * c);
-                double2 qb = *reinterpret_cast<const double2 *>(qs + 4 * c + 2);
-                acc = fma((double)v.x, qa.x, acc); acc = fma((double)v.y, qa.y, acc);
-                acc = fma((double)v.z, qb.x, acc); acc = fma((double)v.w, qb.y, acc);
-            }
-            acc = warp_sum(acc);
-            if (lane == 0) { sd[i] = angular_from_sums(pp[row], qqv, acc); si[i] = id; }
-        }
-        // bitonic sort of P entries under `before`
-        for (int size = 2; size <= P; size <<= 1) {
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                __syncthreads();
-                for (int i = tid; i < (P >> 1); i += kRerankThreads) {
-                    int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
-                    bool asc = (lo & size) == 0;
-                    double dl = sd[lo], dh = sd[hi];
-                    int il = si[lo], ih = si[hi];
-                    bool swap = asc ? before(dh, ih, dl, il) : before(dl, il, dh, ih);
-                    if (swap) { sd[lo] = dh; sd[hi] = dl; si[lo] = ih; si[hi] = il; }
+                const double2 qa = *reinterpret_cast<const double2 *>(qs + 4 * c);
+                const double2 qb = *reinterpret_cast<const double2 *>(qs + 4 * c + 2);
+#pragma unroll
+                for (int u = 0; u < kRows; ++u) {
+                    const float4 v = ldg_stream_f4(src[u] + c);
+                    acc[u] = fma(f32_scaled_f64(v.x), qa.x, acc[u]);
+                    acc[u] = fma(f32_scaled_f64(v.y), qa.y, acc[u]);
+                    acc[u] = fma(f32_scaled_f64(v.z), qb.x, acc[u]);
+                    acc[u] = fma(f32_scaled_f64(v.w), qb.y, acc[u]);
                 }
             }
+            double mine = 0.0;
+            int my_pos = 0;
+            int64_t my_row = 0;
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) {
+                const double s = warp_sum(acc[u]);
+                if (lane == u) { mine = s; my_pos = pos[u]; my_row = row[u]; }
+            }
+            if (lane < kRows && g + lane < m)
+                p.fin_dist[(int64_t)q * p.fcap + my_pos] = angular_from_sums(p.pp[my_row], qqv, mine);
         }
-        __syncthreads();
-        for (int i = tid; i < k; i += kRerankThreads) {
-            bool ok = i < count && i < P && si[i] >= 0;
-            oi[i] = ok ? si[i] : -1;
-            od[i] = ok ? sd[i] : INFINITY;
+    }
+}
+
+// One CTA per query: candidates sorted under the reference order (bitonic network in shared
+// memory), first k written out; short lists are padded with id -1 / +inf.
+__global__ void __launch_bounds__(kOrderThreads)
+rerank_order_kernel(const int32_t *__restrict__ fin_id, const int32_t *__restrict__ fin_cnt,
+                    const double *__restrict__ fin_dist, const uint8_t *__restrict__ overflow, int32_t fcap,
+                    int32_t k, int32_t *__restrict__ out_ids, double *__restrict__ out_dist) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sd = reinterpret_cast<double *>(smem_raw);                 // [P]
+    int *si = reinterpret_cast<int *>(sd + fcap);                      // [P]
+    const int tid = threadIdx.x, q = blockIdx.x;
+    int32_t *oi = out_ids + (int64_t)q * k;
+    double *od = out_dist + (int64_t)q * k;
+    if (overflow[q]) {
+        for (int i = tid; i < k; i += kOrderThreads) { oi[i] = -1; od[i] = INFINITY; }
+        return;
+    }
+    const int count = min(fin_cnt[q], fcap);
+    int P = 32;
+    while (P < count) P <<= 1;
+    for (int i = tid; i < P; i += kOrderThreads) {
+        const bool have = i < count;
+        sd[i] = have ? fin_dist[(int64_t)q * fcap + i] : INFINITY;
+        si[i] = have ? fin_id[(int64_t)q * fcap + i] : -1;
+    }
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = tid; i < (P >> 1); i += kOrderThreads) {
+                int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                bool asc = (lo & size) == 0;
+                double dl = sd[lo], dh = sd[hi];
+                int il = si[lo], ih = si[hi];
+                bool swap = asc ? before(dh, ih, dl, il) : before(dl, il, dh, ih);
+                if (swap) { sd[lo] = dh; sd[hi] = dl; si[lo] = ih; si[hi] = il; }
+            }
         }
+    }
+    __syncthreads();
+    for (int i = tid; i < k; i += kOrderThreads) {
+        bool ok = i < count && si[i] >= 0;
+        oi[i] = ok ? si[i] : -1;
+        od[i] = ok ? sd[i] : INFINITY;
     }
 }
 
@@ -734,6 +840,8 @@ constexpr int kCandCap = 4096, kFinCap = 1024, kPilotMax = kKthMax, kBatchedMaxR
 // tuning knobs for experiments (morna_debug_set_tuning): GEMM variant and pipeline depth
 static int g_gemm_pair = 1;       // 1: CTA pairs (cta_group::2), 0: single CTAs
 static int g_gemm_stages = 4;
+static int g_rerank_rows = 8;     // candidate rows per warp pass of the re-rank (2, 4 or 8)
+static int g_rerank_phase_mb = 0;  // row range kept L2-resident per re-rank phase; 0 = never split into phases
 
 
 static int launch_knn_gemm(const CUtensorMap &tmap_q, const CUtensorMap &tmap_s, const GemmParams &gp, cudaStream_t s) {
@@ -763,7 +871,7 @@ static int launch_knn_gemm(const CUtensorMap &tmap_q, const CUtensorMap &tmap_s,
 }
 
 struct BatchWs {
-    size_t hq, qq, eps, pilot, thr, cand_score, cand_id, cand_cnt, fin_id, fin_cnt, total;
+    size_t hq, qq, eps, pilot, thr, cand_score, cand_id, cand_cnt, fin_id, fin_cnt, fin_dist, total;
     int64_t nq_pad, n0, pilot_ld;
 };
 static BatchWs batch_ws_layout(int64_t n, int64_t nq, int64_t ld_h) {
@@ -783,6 +891,7 @@ static BatchWs batch_ws_layout(int64_t n, int64_t nq, int64_t ld_h) {
     w.cand_cnt = take((size_t)nq * sizeof(int32_t));
     w.fin_id = take((size_t)nq * kFinCap * sizeof(int32_t));
     w.fin_cnt = take((size_t)nq * sizeof(int32_t));
+    w.fin_dist = take((size_t)nq * kFinCap * sizeof(double));
     w.total = off + 1024;
     return w;
 }
@@ -852,7 +961,7 @@ extern "C" int morna_knn_batched_score(const void *hs, int64_t ld_h, const float
         int64_t blocks = (w.nq_pad + 7) / 8;
         if (blocks > (int64_t)sm_count_b() * 8) blocks = (int64_t)sm_count_b() * 8;
         prep_queries_kernel<<<(unsigned)blocks, kPrepThreads, 0, s>>>(queries, nq, w.nq_pad, dim, q_ld, hq, ld_h, qq,
-                                                                    eps, rho_max, eps_acc);
+                                                                    eps, rho_max, eps_acc, overflow, stats);
         MORNA_LAUNCH_CHECK();
     }
     mark();                                                      // 1: queries prepared
@@ -912,15 +1021,37 @@ extern "C" int morna_knn_batched_rerank(const float *vectors, const double *pp, 
     const double *qq = (const double *)(ws + w.qq);
     const int32_t *fin_id = (const int32_t *)(ws + w.fin_id);
     const int32_t *fin_cnt = (const int32_t *)(ws + w.fin_cnt);
-    const size_t rr_smem = (size_t)ld * sizeof(double) + (size_t)kFinCap * (sizeof(double) + sizeof(int));
+    RerankParams rp{};
+    rp.vectors = vectors; rp.pp = pp; rp.ld = ld; rp.dim = dim; rp.id_base = id_base; rp.n = (int32_t)n;
+    rp.queries = queries; rp.q_ld = q_ld; rp.qq = qq; rp.fin_id = fin_id; rp.fin_cnt = fin_cnt; rp.overflow = overflow;
+    rp.fcap = kFinCap; rp.nq = (int32_t)nq; rp.fin_dist = (double *)(ws + w.fin_dist);
+    // phases: only when a row is re-ranked several times per batch (otherwise every row is read at
+    // most about once and splitting would only re-stage the queries)
+    rp.phases = 1; rp.phase_rows = (int32_t)n;
+    const double reuse = (double)nq * (1.2 * k) / (double)n;
+    if (g_rerank_phase_mb > 0 && reuse >= 3.0) {
+        int64_t rows = ((int64_t)g_rerank_phase_mb << 20) / ((int64_t)ld * 4);
+        if (rows < 1024) rows = 1024;
+        if (rows < n) {
+            rp.phases = (int32_t)((n + rows - 1) / rows);
+            rp.phase_rows = (int32_t)((n + rp.phases - 1) / rp.phases);
+        }
+    }
+    const size_t rr_smem = (size_t)ld * sizeof(double) + (size_t)kFinCap * sizeof(int);
     if (rr_smem > 200 * 1024) return MORNA_ERR_INVALID_ARGUMENT;
-    if (rr_smem > 48 * 1024)
-        MORNA_CUDA_TRY(cudaFuncSetAttribute(rerank_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)rr_smem));
-    const unsigned rr_grid = (unsigned)(nq < 2 * sm_count_b() ? nq : 2 * sm_count_b());
-    rerank_select_kernel<<<rr_grid, kRerankThreads, rr_smem, s>>>(vectors, pp, ld, dim, id_base, queries, q_ld, qq,
-                                                                  fin_id, fin_cnt, overflow, kFinCap, k, (int32_t)nq,
-                                                                  out_ids, out_dist);
+    auto kern = g_rerank_rows == 8 ? rerank_dist_kernel<8> : g_rerank_rows == 2 ? rerank_dist_kernel<2> : rerank_dist_kernel<4>;
+    MORNA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
+    int per_sm = 0;
+    MORNA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRrThreads, rr_smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t items = (int64_t)nq * rp.phases;
+    int64_t rr_grid = (int64_t)per_sm * sm_count_b();
+    if (rr_grid > items) rr_grid = items;
+    kern<<<(unsigned)rr_grid, kRrThreads, rr_smem, s>>>(rp);
+    MORNA_LAUNCH_CHECK();
+    const size_t or_smem = (size_t)kFinCap * (sizeof(double) + sizeof(int));
+    rerank_order_kernel<<<(unsigned)nq, kOrderThreads, or_smem, s>>>(fin_id, fin_cnt, rp.fin_dist, overflow, kFinCap, k,
+                                                                    out_ids, out_dist);
     MORNA_LAUNCH_CHECK();
     return MORNA_OK;
 }
@@ -958,7 +1089,7 @@ extern "C" int morna_debug_tensor_scores(const void *hs, int64_t ld_h, const flo
     const float eps_acc = (float)((double)(dim / 16 + 8) * 2.384185791015625e-07 * 1.01);
     int64_t blocks = (w.nq_pad + 7) / 8;
     prep_queries_kernel<<<(unsigned)blocks, kPrepThreads, 0, s>>>(queries, nq, w.nq_pad, dim, q_ld, hq, ld_h, qq,
-                                                                eps_out, rho_max, eps_acc);
+                                                                eps_out, rho_max, eps_acc, nullptr, nullptr);
     MORNA_LAUNCH_CHECK();
     CUtensorMap tmap_q, tmap_s;
     int rc = make_tmap(&tmap_q, hq, (uint64_t)w.nq_pad, (uint64_t)ld_h, gemm::BM);
@@ -981,6 +1112,8 @@ extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
     else if (key == 3) morna::set_single_tma(value);
     else if (key == 4) morna::set_acc_pipelined(value);
     else if (key == 1) g_gemm_stages = value;
+    else if (key == 5) g_rerank_rows = value;
+    else if (key == 6) g_rerank_phase_mb = value;
 
     else return MORNA_ERR_INVALID_ARGUMENT;
     return MORNA_OK;

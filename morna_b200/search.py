@@ -196,8 +196,58 @@ class MornaSearch(object):
             _lib.check(self.lib.morna_prepare_tensor_operand(
                 _lib.dev_ptr(self.vectors), _lib.dev_ptr(self.pp), n, self.dim, self.ld, _lib.dev_ptr(self.hs),
                 self.ld_h, _lib.dev_ptr(self.rho_max), _lib.stream_ptr()), "morna_prepare_tensor_operand")
-        self._bws = None
+        self._bws = {}
         self.last_stats = None
+
+    def _batched_launch(self, queries, k, stream=None, phase_events=None):
+        """Enqueues morna_knn_batched for every row block; no host synchronisation.  Returns the
+        per-block (b0, b1, ids, dists, overflow, stats) device tensors."""
+        nq, dev = queries.shape[0], self.device
+        n = self.row_hi - self.row_lo
+        sid = (stream if stream is not None else torch.cuda.current_stream(dev)).cuda_stream
+        parts = []
+        with torch.cuda.device(dev):
+            for b0 in range(0, n, self.BATCH_BLOCK_ROWS):
+                b1 = min(n, b0 + self.BATCH_BLOCK_ROWS)
+                out_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+                out_d = torch.empty((nq, k), dtype=torch.float64, device=dev)
+                overflow = torch.empty(nq, dtype=torch.uint8, device=dev)
+                stats = torch.empty(4, dtype=torch.int32, device=dev)
+                need = self.lib.morna_knn_batched_workspace_bytes(b1 - b0, nq, self.dim, k)
+                ws = self._bws.get(sid)                # one workspace per stream: batches in flight do not share
+                if ws is None or ws.numel() < need:
+                    ws = self._bws[sid] = _lib.workspace(need, dev)
+                _lib.check(self.lib.morna_knn_batched(
+                    _lib.dev_ptr(self.vectors[b0:b1]), _lib.dev_ptr(self.pp[b0:b1]), _lib.dev_ptr(self.hs[b0:b1]),
+                    self.ld_h, _lib.dev_ptr(self.rho_max), b1 - b0, self.dim, self.ld, self.row_lo + b0,
+                    _lib.ptr(queries), nq, self.dim, k, _lib.dev_ptr(out_ids), _lib.dev_ptr(out_d),
+                    _lib.dev_ptr(overflow), _lib.dev_ptr(stats), _lib.dev_ptr(ws), ws.numel(),
+                    phase_events, _lib.stream_ptr(stream)), "morna_knn_batched")
+                parts.append((b0, b1, out_ids, out_d, overflow, stats))
+        return parts
+
+    def _batched_finish(self, parts, queries, k, stream=None, host_stats=None):
+        """Host half: queries whose candidate lists overflowed (ties wider than the lists) are answered
+        by the exact scan, then the row blocks' lists are merged.  `host_stats`: stats already copied
+        to the host, one [4] int tensor per block; otherwise they are read here (synchronises)."""
+        from . import dist as mdist
+        stats_total = torch.zeros(4, dtype=torch.int64)
+        for i, (b0, b1, out_ids, out_d, overflow, stats) in enumerate(parts):
+            st = host_stats[i] if host_stats is not None else stats.cpu()
+            stats_total += st.to(torch.int64)
+            if int(st[0]) > 0:
+                idx = overflow.nonzero().flatten()
+                sub = MornaSearch.__new__(MornaSearch)
+                sub.__dict__.update(self.__dict__)
+                sub.vectors, sub.pp = self.vectors[b0:b1], self.pp[b0:b1]
+                sub.row_lo, sub.row_hi, sub._ws = self.row_lo + b0, self.row_lo + b1, None
+                e_ids, e_d = sub.exact_search_device(queries[idx], k, stream, allow_single=False)
+                out_ids[idx] = e_ids
+                out_d[idx] = e_d
+        self.last_stats = stats_total.tolist()
+        if len(parts) == 1:
+            return parts[0][2], parts[0][3]
+        return mdist.merge_topk(torch.cat([p[2] for p in parts], 1), torch.cat([p[3] for p in parts], 1), k, stream)
 
     def batched_search_device(self, queries, k, stream=None, check_overflow=True, phase_events=None):
         """Same contract and same results as exact_search_device, with the N x D
@@ -208,46 +258,35 @@ class MornaSearch(object):
         self.enable_tensor_path()
         assert queries.is_cuda and queries.dtype == torch.float64 and queries.dim() == 2
         queries = queries.contiguous()
-        nq, dev = queries.shape[0], self.device
+        nq = queries.shape[0]
         n = self.row_hi - self.row_lo
         assert queries.shape[1] == self.dim
         if n == 0 or nq == 0 or k > 512:
             return self.exact_search_device(queries, k, stream)
-        parts = []
-        stats_total = torch.zeros(4, dtype=torch.int64)
-        with torch.cuda.device(dev):
-            for b0 in range(0, n, self.BATCH_BLOCK_ROWS):
-                b1 = min(n, b0 + self.BATCH_BLOCK_ROWS)
-                out_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
-                out_d = torch.empty((nq, k), dtype=torch.float64, device=dev)
-                overflow = torch.empty(nq, dtype=torch.uint8, device=dev)
-                stats = torch.empty(4, dtype=torch.int32, device=dev)
-                need = self.lib.morna_knn_batched_workspace_bytes(b1 - b0, nq, self.dim, k)
-                if self._bws is None or self._bws.numel() < need:
-                    self._bws = _lib.workspace(need, dev)
-                _lib.check(self.lib.morna_knn_batched(
-                    _lib.dev_ptr(self.vectors[b0:b1]), _lib.dev_ptr(self.pp[b0:b1]), _lib.dev_ptr(self.hs[b0:b1]),
-                    self.ld_h, _lib.dev_ptr(self.rho_max), b1 - b0, self.dim, self.ld, self.row_lo + b0,
-                    _lib.ptr(queries), nq, self.dim, k, _lib.dev_ptr(out_ids), _lib.dev_ptr(out_d),
-                    _lib.dev_ptr(overflow), _lib.dev_ptr(stats), _lib.dev_ptr(self._bws), self._bws.numel(),
-                    phase_events, _lib.stream_ptr(stream)), "morna_knn_batched")
-                if check_overflow:
-                    st = stats.cpu()
-                    stats_total += st.to(torch.int64)
-                    if int(st[0]) > 0:                 # rare: ties wider than the candidate lists
-                        idx = overflow.nonzero().flatten()
-                        sub = MornaSearch.__new__(MornaSearch)
-                        sub.__dict__.update(self.__dict__)
-                        sub.vectors, sub.pp = self.vectors[b0:b1], self.pp[b0:b1]
-                        sub.row_lo, sub.row_hi, sub._ws = self.row_lo + b0, self.row_lo + b1, None
-                        e_ids, e_d = sub.exact_search_device(queries[idx], k, stream)
-                        out_ids[idx] = e_ids
-                        out_d[idx] = e_d
-                parts.append((out_ids, out_d))
-        self.last_stats = stats_total.tolist()
+        parts = self._batched_launch(queries, k, stream, phase_events)
+        if check_overflow:
+            return self._batched_finish(parts, queries, k, stream)
         if len(parts) == 1:
-            return parts[0]
-        return mdist.merge_topk(torch.cat([p[0] for p in parts], 1), torch.cat([p[1] for p in parts], 1), k, stream)
+            return parts[0][2], parts[0][3]
+        return mdist.merge_topk(torch.cat([p[2] for p in parts], 1), torch.cat([p[3] for p in parts], 1), k, stream)
+
+    def search_batches(self, batches, k, depth=2):
+        """Streams query batches through the GPU: generator over ``batches`` (each a numpy
+        [nq x dim] float32/float64 array) yielding ``(ids, dists)`` numpy arrays in order -- the same
+        results as ``exact_search_batch`` per batch.  ``depth`` batches are in flight, each on its own
+        CUDA stream with its own pinned staging buffers and workspace, so batch i+1's host->device
+        copy and batch i-1's device->host copy overlap batch i's kernels."""
+        pipe = BatchPipeline(self, k, depth)
+        pending = 0
+        for q in batches:
+            if pending == depth:
+                yield pipe.collect()
+                pending -= 1
+            pipe.submit(q)
+            pending += 1
+        while pending:
+            yield pipe.collect()
+            pending -= 1
 
     def exact_search_batch(self, queries, k, tensor_cores=None):
         """Host entry: queries numpy [nq x dim] (float32 or float64) -> numpy (ids, dists).
@@ -310,3 +349,86 @@ class MornaSearch(object):
             out.append(cur.fetchone())
         conn.close()
         return out
+
+
+class _PipeSlot(object):
+    pass
+
+
+class BatchPipeline(object):
+    """``depth`` query batches in flight on one MornaSearch (see MornaSearch.search_batches).
+    submit() enqueues pinned-host -> device copy, the batched search and the device -> pinned-host copy
+    of ids, distances and the overflow counters on the slot's stream and returns at once; collect()
+    waits for the oldest batch and returns host arrays (views of the slot's pinned buffers, valid until
+    the slot is reused ``depth`` submits later)."""
+
+    def __init__(self, search, k, depth=2):
+        self.search, self.k, self.depth = search, k, depth
+        search.enable_tensor_path()
+        self.slots = []
+        for _ in range(depth):
+            sl = _PipeSlot()
+            sl.stream = torch.cuda.Stream(device=search.device)
+            sl.done = torch.cuda.Event()
+            sl.nq = -1
+            self.slots.append(sl)
+        self.head = self.tail = 0           # next slot to submit into / to collect from
+
+    def _size(self, sl, nq, dtype):
+        s, k = self.search, self.k
+        if sl.nq == nq and sl.host_q.dtype == dtype:
+            return
+        sl.nq = nq
+        sl.host_q = torch.empty((nq, s.dim), dtype=dtype).pin_memory()
+        sl.host_ids = torch.empty((nq, k), dtype=torch.int32).pin_memory()
+        sl.host_d = torch.empty((nq, k), dtype=torch.float64).pin_memory()
+        sl.host_stats = torch.empty((1 + (s.row_hi - s.row_lo - 1) // s.BATCH_BLOCK_ROWS, 4), dtype=torch.int32).pin_memory()
+
+    def submit(self, queries):
+        s, k = self.search, self.k
+        sl = self.slots[self.head % self.depth]
+        assert self.head - self.tail < self.depth, "collect() before submitting more than `depth` batches"
+        self.head += 1
+        q = torch.from_numpy(np.ascontiguousarray(queries)) if isinstance(queries, np.ndarray) else queries
+        if q.dtype != torch.float32:
+            q = q.to(torch.float64)
+        self._size(sl, q.shape[0], q.dtype)
+        if q.is_pinned() and q.is_contiguous():
+            src = q                          # already page-locked: copied straight from the caller's buffer,
+        else:                                # which must stay untouched until collect()
+            sl.host_q.copy_(q)               # pageable source -> the slot's pinned staging buffer
+            src = sl.host_q
+        with torch.cuda.stream(sl.stream):
+            sl.qd = src.to(s.device, non_blocking=True).to(torch.float64)          # float32 widens exactly
+            n = s.row_hi - s.row_lo
+            if n == 0 or sl.nq == 0 or k > 512:
+                sl.parts = None
+                ids, d = s.exact_search_device(sl.qd, k)
+            else:
+                sl.parts = s._batched_launch(sl.qd, k)
+                for i, part in enumerate(sl.parts):
+                    sl.host_stats[i].copy_(part[5], non_blocking=True)
+                ids, d = sl.parts[0][2], sl.parts[0][3]
+            sl.simple = sl.parts is None or len(sl.parts) == 1
+            if sl.simple:
+                sl.host_ids.copy_(ids, non_blocking=True)
+                sl.host_d.copy_(d, non_blocking=True)
+            sl.done.record(sl.stream)
+
+    def collect(self):
+        s, k = self.search, self.k
+        assert self.tail < self.head, "nothing in flight"
+        sl = self.slots[self.tail % self.depth]
+        self.tail += 1
+        sl.done.synchronize()
+        if sl.parts is not None:
+            overflowed = int(sl.host_stats[:len(sl.parts), 0].sum()) > 0
+            if overflowed or not sl.simple:  # rare: exact-scan fix-up and/or merge of row blocks, then copy again
+                with torch.cuda.stream(sl.stream):
+                    ids, d = s._batched_finish(sl.parts, sl.qd, k, host_stats=[sl.host_stats[i] for i in range(len(sl.parts))])
+                    sl.host_ids.copy_(ids, non_blocking=True)
+                    sl.host_d.copy_(d, non_blocking=True)
+                sl.stream.synchronize()
+            else:
+                s.last_stats = sl.host_stats[0].to(torch.int64).tolist()
+        return sl.host_ids.numpy(), sl.host_d.numpy()

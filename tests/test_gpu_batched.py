@@ -142,3 +142,77 @@ def test_batched_row_blocks_merge():
     e_ids, e_d = srch.exact_search_device(q, 30)
     b_ids, b_d = srch.batched_search_device(q, 30)
     assert torch.equal(b_ids, e_ids) and torch.equal(b_d, e_d)
+
+
+@pytest.mark.parametrize("rows_per_warp,phase_mb", [(2, 0), (4, 1), (8, 0), (8, 1), (4, 0)])
+def test_rerank_variants_agree(rows_per_warp, phase_mb):
+    """Rows per warp pass and the L2 phase split only change the schedule of the re-rank, never a bit."""
+    from morna_b200 import _lib
+    lib = _lib.load()
+    try:
+        assert lib.morna_debug_set_tuning(5, rows_per_warp) == 0 and lib.morna_debug_set_tuning(6, phase_mb) == 0
+        rng = np.random.default_rng(123)
+        n, d, nq, k = 4100, 300, 600, 50          # every row is re-ranked ~9 times: the phase split engages
+        S = rng.standard_normal((n, d)).astype(np.float32)
+        S[7, :5] = np.float32(1e-42)              # float32 denormals and signed zeros survive f32_scaled_f64
+        S[8, :5] = np.float32(-0.0)
+        srch = make_search(S)
+        Q = S[rng.permutation(n)[:nq]].astype(np.float64) + 0.02 * rng.standard_normal((nq, d))
+        Q[0] = S[7]
+        Q[1, :] = 0.0
+        Q[1, :5] = 1e-42
+        q = torch.from_numpy(Q).cuda()
+        e_ids, e_d = srch.exact_search_device(q, k)
+        b_ids, b_d = srch.batched_search_device(q, k)
+        assert torch.equal(b_ids, e_ids) and torch.equal(b_d, e_d)
+    finally:
+        lib.morna_debug_set_tuning(5, 8)
+        lib.morna_debug_set_tuning(6, 0)
+
+
+def test_queries_too_large_for_the_scaled_rerank_go_to_the_exact_scan():
+    rng = np.random.default_rng(9)
+    n, d, nq, k = 3000, 128, 70, 10
+    S = rng.standard_normal((n, d)).astype(np.float32)
+    srch = make_search(S)
+    Q = rng.standard_normal((nq, d))
+    Q[3, 5] = 3e38                 # >= 2^127: q * 2^896 would overflow a double
+    Q[11] *= 1e300
+    q = torch.from_numpy(Q).cuda()
+    e_ids, e_d = srch.exact_search_device(q, k)
+    b_ids, b_d = srch.batched_search_device(q, k)
+    assert srch.last_stats[0] == 2
+    assert torch.equal(b_ids, e_ids) and torch.equal(b_d, e_d)
+
+
+def test_streaming_batches_equal_the_synchronous_call():
+    """MornaSearch.search_batches: several batches in flight on their own streams, same results."""
+    rng = np.random.default_rng(31)
+    n, d, k = 6000, 200, 25
+    S = rng.standard_normal((n, d)).astype(np.float32)
+    S[10:14] = S[9]                                  # a few exact ties
+    srch = make_search(S)
+    batches = []
+    for b, nq in enumerate((300, 300, 64, 500, 300)):
+        Q = S[rng.permutation(n)[:nq]] + np.float32(0.03) * rng.standard_normal((nq, d)).astype(np.float32)
+        Q[0] = S[9]
+        batches.append(Q if b % 2 == 0 else Q.astype(np.float64))
+    batches.append(torch.from_numpy(batches[0]).pin_memory())        # caller-pinned source, no staging copy
+    want = [srch.exact_search_batch(np.asarray(B), k, tensor_cores=False) for B in batches]
+    for depth in (1, 2, 3):
+        got = [(i.copy(), d_.copy()) for i, d_ in srch.search_batches(iter(batches), k, depth=depth)]
+        assert len(got) == len(want)
+        for (gi, gd), (wi, wd) in zip(got, want):
+            assert np.array_equal(gi, wi) and np.array_equal(gd, wd)
+
+
+def test_streaming_batches_handle_tie_overflow_and_row_blocks():
+    oracle = mo.go_index(tiny_lines(), features=3000, sample_threshold=100)
+    S = oracle.matrix_f32()
+    srch = make_search(S)
+    srch.BATCH_BLOCK_ROWS = 4096                     # two row blocks + merge, and thousands of ties at distance 0
+    rows = np.array([0, 2040, 6595, 5, 4000, 17] * 12)
+    B = S[rows]
+    wi, wd = srch.exact_search_batch(B, 20, tensor_cores=False)
+    for gi, gd in srch.search_batches([B, B.astype(np.float64)], 20):
+        assert np.array_equal(gi, wi) and np.array_equal(gd, wd)
