@@ -152,13 +152,19 @@ int morna_knn_exact(const float *vectors, const double *pp, int64_t n, int32_t d
                     int32_t *out_ids, double *out_dist,
                     void *workspace, size_t workspace_bytes, void *stream);
 
-/* exact_search_nn for ONE query, HBM-bound: an FP32 scan streams the rows once (4*n*ld bytes), the
- * rows whose FP32 score is within a rigorous rounding bound of the k-th best are re-ranked with
- * the FP64 sums of morna_knn_exact, so ids and distances are identical to it.
+/* exact_search_nn for ONE query, HBM-bound, one kernel: every warp streams its share of the rows once
+ * (4*n*ld bytes) and computes each row's exact distance with the FP64 sums of morna_knn_exact; the
+ * last CTA to finish selects the k nearest under the reference order from a float key per row and
+ * the stored doubles, so ids and distances are identical to morna_knn_exact.
  *   query    [dev] double[dim]
- *   fallback [dev] int32[1]  out: 1 if ties overflowed the candidate list (outputs then hold
- *                            nothing valid and morna_knn_exact must answer), else 0 */
+ *   fallback [dev] int32[1]  out: 1 if ties overflowed the candidate list or a query value is
+ *                            >= 2^127 in magnitude (outputs then hold nothing valid and
+ *                            morna_knn_exact must answer), else 0
+ * The first 256 bytes of the workspace are a control block that must be zero before the first call
+ * (morna_knn_single_workspace_init); every call leaves it zero again, so a workspace is
+ * initialised once and reused.  One call at a time per workspace. */
 size_t morna_knn_single_workspace_bytes(int64_t n);
+int morna_knn_single_workspace_init(void *workspace, size_t workspace_bytes, void *stream);
 int morna_knn_single(const float *vectors, const double *pp, int64_t n, int32_t dim, int64_t ld,
                      int32_t id_base, const double *query, int32_t k, int32_t *out_ids, double *out_dist,
                      int32_t *fallback, void *workspace, size_t workspace_bytes, void *stream);

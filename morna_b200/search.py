@@ -148,6 +148,8 @@ class MornaSearch(object):
             if getattr(self, "_sws", None) is None or self._sws.numel() < need:
                 self._sws = _lib.workspace(need, dev)
                 self._sfallback = torch.zeros(1, dtype=torch.int32, device=dev)
+                _lib.check(self.lib.morna_knn_single_workspace_init(_lib.dev_ptr(self._sws), self._sws.numel(),
+                                                                    _lib.stream_ptr(stream)), "morna_knn_single_workspace_init")
             _lib.check(self.lib.morna_knn_single(
                 _lib.dev_ptr(self.vectors), _lib.dev_ptr(self.pp), n, self.dim, self.ld, self.row_lo,
                 _lib.ptr(query), k, _lib.dev_ptr(out_ids), _lib.dev_ptr(out_d), _lib.dev_ptr(self._sfallback),

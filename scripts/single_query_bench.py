@@ -13,7 +13,7 @@ except Exception:
     pass
 flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 K, D = 100, 3000
-for N in (21504, 50000, 125000):
+for N in [int(a) for a in sys.argv[1:]] or (21504, 50000, 125000):
     g = torch.Generator(device='cuda'); g.manual_seed(1234)
     S = torch.randn((N, D), generator=g, device='cuda')
     s = MornaSearch(vectors=S, stats=(N, N, D))
@@ -30,13 +30,14 @@ for N in (21504, 50000, 125000):
     def both():
         return s.exact_search_device(q, K, allow_single=False)
     sws = _lib.workspace(lib.morna_knn_single_workspace_bytes(N), 'cuda'); fb = torch.zeros(1, dtype=torch.int32, device='cuda')
+    _lib.check(lib.morna_knn_single_workspace_init(_lib.dev_ptr(sws), sws.numel(), _lib.stream_ptr()), 'init')
     def single():
         _lib.check(lib.morna_knn_single(_lib.dev_ptr(s.vectors), _lib.dev_ptr(s.pp), N, D, s.ld, 0, _lib.dev_ptr(q), K,
                                         _lib.dev_ptr(oi), _lib.dev_ptr(od), _lib.dev_ptr(fb), _lib.dev_ptr(sws), sws.numel(),
                                         _lib.stream_ptr()), "single")
     res = {}
     def single_ldg():
-        lib.morna_debug_set_tuning(3, 0); single(); lib.morna_debug_set_tuning(3, 1)
+        lib.morna_debug_set_tuning(3, 4); single(); lib.morna_debug_set_tuning(3, 0)
     graphs = {}
     def graphed(name, fn):
         """Replay the call from a CUDA graph so host launch overhead stays out of the device timeline."""
@@ -70,13 +71,19 @@ for N in (21504, 50000, 125000):
                 pre(); e0.record(); single_g(); e1.record(); torch.cuda.synchronize(); tot += e0.elapsed_time(e1) / reps
         res["g_" + label] = tot * 1e3
         print("N=%d: graph replay, %s: %.1f us -> %.0f%% of the HBM floor" % (N, label, tot * 1e3, 100 * (4.0 * N * D / (peak * 1e9) * 1e6) / (tot * 1e3)))
+    for _ in range(3):
+        single(); torch.cuda.synchronize()
+        st = sws[16:80].view(torch.int64).cpu().tolist()
+        print("N=%d: in-kernel stamps: scan %.1f us, k-th key %.1f us (pivot %.1f, filter %.1f, k-th of survivors %.1f, emit %.1f), sort+write %.1f us" % (
+              N, (st[1] - st[0]) / 1e3, (st[2] - st[1]) / 1e3, (st[4] - st[1]) / 1e3, (st[5] - st[4]) / 1e3, (st[6] - st[5]) / 1e3,
+              (st[2] - st[6]) / 1e3, (st[3] - st[2]) / 1e3))
     ids, d = both()
     assert int(ids[0, 0]) == N // 3 and float(d[0, 0]) == 0.0
     single(); torch.cuda.synchronize()
     assert int(fb.item()) == 0 and torch.equal(oi, ids) and torch.equal(od, d)
-    print("N=%d: fp32-scan path replayed from a CUDA graph %.1f us -> %.0f q/s, %.0f%% of the HBM floor" % (
+    print("N=%d: fused fp64 scan+select replayed from a CUDA graph %.1f us -> %.0f q/s, %.0f%% of the HBM floor" % (
           N, res["single_graph"], 1e6 / res["single_graph"], 100 * (4.0 * N * D / (peak * 1e9) * 1e6) / res["single_graph"]))
-    print("N=%d: fp32-scan path (bulk-copy staged) %.1f us -> %.0f q/s, %.0f%% of the HBM floor; per-warp loads %.1f us" % (
+    print("N=%d: fused fp64 scan+select (stream launch) %.1f us -> %.0f q/s, %.0f%% of the HBM floor; forced 4 rows/pass %.1f us" % (
           N, res["single"], 1e6 / res["single"], 100 * (4.0 * N * D / (peak * 1e9) * 1e6) / res["single"], res["single_ldg"]))
     floor = 4.0 * N * D / (peak * 1e9) * 1e6
     print("N=%d: scan %.1f us (%.0f GB/s, %.0f%% of %.0f), select %.1f us, scan+select %.1f us -> %.0f q/s, %.0f%% of the HBM floor %.1f us"

@@ -338,20 +338,37 @@ def test_cli_index_then_exact_search_of_in_index_sample(tmp_path):
         cli.main(["search", "-x", base, "-q", "999999", "-e"], stdout=io.StringIO())
 
 
-# ------------------------------------------------------------------ single query, FP32 scan + FP64 re-rank
+# ------------------------------------------------------------------ single query, fused FP64 scan + select
 @pytest.mark.parametrize("n,d,k", [(21504, 3000, 100), (3000, 3000, 20), (5000, 130, 100), (900, 37, 64), (40, 16, 100)])
 def test_single_query_path_equals_fp64_scan(n, d, k):
     _run_single_query_checks(n, d, k)
 
 
-def test_single_query_per_warp_load_variant():
+@pytest.mark.parametrize("rows_per_pass", [1, 2, 3, 4, 5])
+def test_single_query_rows_per_pass_variants(rows_per_pass):
     from morna_b200 import _lib
     lib = _lib.load()
     try:
-        assert lib.morna_debug_set_tuning(3, 0) == 0
-        _run_single_query_checks(7000, 300, 100)
+        assert lib.morna_debug_set_tuning(3, rows_per_pass) == 0
+        _run_single_query_checks(7001, 300, 100)
     finally:
-        lib.morna_debug_set_tuning(3, 1)
+        lib.morna_debug_set_tuning(3, 0)
+
+
+def test_single_query_many_rows_per_warp_and_huge_query_values():
+    _run_single_query_checks(60011, 64, 100)          # more rows than one pass of every resident warp
+    rng = np.random.default_rng(1)
+    S = rng.standard_normal((900, 40)).astype(np.float32)
+    srch = make_search(S)
+    qv = rng.standard_normal(40)
+    qv[3] = 2e38                                      # q * 2^896 is not finite: the generic scan answers
+    q = torch.from_numpy(qv).cuda()
+    s_ids, s_d = srch.single_search_device(q, 10)
+    assert int(srch._sfallback.item()) == 1
+    e_ids, e_d = srch.exact_search_device(q.view(1, -1), 10, allow_single=False)
+    assert torch.equal(s_ids, e_ids) and torch.equal(s_d, e_d)
+    s_ids, s_d = srch.single_search_device(torch.from_numpy(S[5].astype(np.float64)).cuda(), 10)
+    assert int(srch._sfallback.item()) == 0 and int(s_ids[0, 0]) == 5      # the workspace is reusable afterwards
 
 
 def _run_single_query_checks(n, d, k):
