@@ -89,19 +89,23 @@ int morna_assign_internal_ids(const int64_t *row_off, const uint8_t *pass, int64
 /* Scatter-add of sign * (coverage * idf) into per-sample vectors.  Replaces the
  * per-pair loop at morna.py:376-388.  Sums are double and every (sample, bucket)
  * cell is accumulated in file row order, so cells equal the reference's Python
- * floats bit for bit (when a row does not list the same sample twice).
+ * floats bit for bit (when a row does not list the same sample twice).  Rows whose
+ * sample ids are strictly ascending (as intropolis writes them) take the fast path:
+ * one warp per (bucket, sample-id range), no block barriers; any other input takes the
+ * barrier-per-row path with the same results.
  * The accumulator is bucket-major: acc[b * acc_ld + (internal_id - id_lo)], and
  * only internal ids in [id_lo, id_hi) are accumulated (multi-GPU shards by id
  * range, each rank streaming the same rows).  The call zero-fills acc itself.
  *   bucket/sign/idf  [dev] per-row, from morna_hash_junctions / morna_idf_host
  *   cov              [dev] int32[nnz] coverages
+ *   id_of_sample     [dev] int32[max_sample_id + 1] from morna_assign_internal_ids
  *   acc              [dev] double[dim * acc_ld], acc_ld >= id_hi - id_lo
  */
 size_t morna_index_accumulate_workspace_bytes(int64_t n_rows, int32_t dim);
 int morna_index_accumulate(const int64_t *row_off, const uint8_t *pass, const int32_t *bucket,
                            const int8_t *sign, const double *idf, int64_t n_rows,
                            const int32_t *sample, const int32_t *cov, int64_t nnz,
-                           const int32_t *id_of_sample, int32_t id_lo, int32_t id_hi,
+                           const int32_t *id_of_sample, int32_t max_sample_id, int32_t id_lo, int32_t id_hi,
                            int32_t dim, double *acc, int64_t acc_ld,
                            void *workspace, size_t workspace_bytes, void *stream);
 

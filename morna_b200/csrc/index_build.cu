@@ -155,7 +155,7 @@ constexpr int kAccTile = 24576;   // doubles of one bucket column held in shared
 // in file order with a barrier between rows, so each cell sees its addends in the
 // reference's order (morna.py:376-388) and the double sums are bit-identical.
 __global__ void __launch_bounds__(kAccThreads)
-index_accumulate_kernel(const int64_t *__restrict__ row_off, const int8_t *__restrict__ sign,
+index_accumulate_kernel(const int32_t *__restrict__ use_flag, const int64_t *__restrict__ row_off, const int8_t *__restrict__ sign,
                         const double *__restrict__ idf, const int32_t *__restrict__ sample,
                         const int32_t *__restrict__ cov, const int32_t *__restrict__ id_of_sample,
                         const int32_t *__restrict__ rows_by_bucket, const int32_t *__restrict__ bucket_begin,
@@ -168,6 +168,7 @@ index_accumulate_kernel(const int64_t *__restrict__ row_off, const int8_t *__res
     const int32_t width = hi - lo;
     const int32_t r_begin = bucket_begin[b], r_end = bucket_begin[b + 1];
     double *out = acc + (int64_t)b * acc_ld + (lo - id_lo);
+    if (use_flag && !*use_flag) return;      // the sample-range variant answers
     if (r_begin == r_end) return;            // acc was zero-filled by the caller
     for (int i = threadIdx.x; i < width; i += kAccThreads) col[i] = 0.0;
     __syncthreads();
@@ -200,36 +201,55 @@ constexpr int kAcc2Tile = 22528;          // doubles of the bucket column per CT
 constexpr size_t kAcc2MetaBytes = (size_t)kAcc2Window * (8 + 8) + (size_t)(kAcc2Window + 1) * 4 + 16;
 
 __global__ void __launch_bounds__(256)
-sorted_row_len_kernel(const int64_t *__restrict__ row_off, const int32_t *__restrict__ rows_by_bucket, int64_t n_rows,
-                      int64_t *__restrict__ len) {
+sorted_row_len_kernel(const int32_t *__restrict__ use_flag, const int64_t *__restrict__ row_off,
+                      const int32_t *__restrict__ rows_by_bucket, int64_t n_rows, int64_t *__restrict__ len) {
+    if (use_flag && !*use_flag) return;      // the sample-range variant answers
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) {
         const int32_t j = rows_by_bucket[i];
         len[i] = row_off[j + 1] - row_off[j];
     }
 }
 
-// rows whose sample ids are strictly increasing or strictly decreasing cannot list a sample twice
+// rows whose sample ids are strictly increasing or strictly decreasing cannot list a sample twice;
+// flags[0] = some passing row is neither, flags[1] = some passing row is not strictly increasing
 __global__ void __launch_bounds__(256)
 rows_monotonic_kernel(const int64_t *__restrict__ row_off, const uint8_t *__restrict__ pass, int64_t n_rows,
-                      const int32_t *__restrict__ sample, int32_t *__restrict__ not_monotonic) {
+                      const int32_t *__restrict__ sample, int32_t *__restrict__ flags) {
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n_rows; j += warps_total) {
         if (!pass[j]) continue;
         const int64_t b = row_off[j], e = row_off[j + 1];
         bool up = true, down = true;
-        for (int64_t p = b + 1 + lane; p < e; p += 32) {
-            const int32_t a = sample[p - 1], c = sample[p];
-            up &= c > a; down &= c < a;
+        int32_t carry = 0;
+        for (int64_t p0 = b; p0 < e; p0 += 128) {          // four independent chunks in flight
+            int32_t c[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t p = p0 + 32 * u + lane;
+                c[u] = p < e ? __ldg(sample + p) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t p = p0 + 32 * u + lane;
+                int32_t a = __shfl_up_sync(kFull, c[u], 1);
+                if (lane == 0) a = carry;
+                carry = __shfl_sync(kFull, c[u], 31);
+                const bool have = p < e && p > b;          // the row's first pair has no predecessor
+                up &= !have || c[u] > a; down &= !have || c[u] < a;
+            }
         }
+        if (lane == 0 && e > b) up &= sample[b] >= 0;       // (negative ids would index before the slices)
         up = __all_sync(kFull, up); down = __all_sync(kFull, down);
-        if (lane == 0 && !up && !down) *not_monotonic = 1;
+        if (lane == 0 && !up && !down) flags[0] = 1;
+        if (lane == 0 && !up) flags[1] = 1;
     }
 }
 
 template <bool kAtomic>
 __global__ void __launch_bounds__(kAcc2Threads)
-index_accumulate2_kernel(const int32_t *__restrict__ run_flag, const int64_t *__restrict__ row_off, const int8_t *__restrict__ sign,
+index_accumulate2_kernel(const int32_t *__restrict__ use_flag, const int32_t *__restrict__ run_flag,
+                         const int64_t *__restrict__ row_off, const int8_t *__restrict__ sign,
                          const double *__restrict__ idf, const int32_t *__restrict__ sample,
                          const int32_t *__restrict__ cov, const int32_t *__restrict__ id_of_sample,
                          const int32_t *__restrict__ rows_by_bucket, const int32_t *__restrict__ bucket_begin,
@@ -249,6 +269,7 @@ index_accumulate2_kernel(const int32_t *__restrict__ run_flag, const int64_t *__
     const int32_t r_begin = bucket_begin[b], r_end = bucket_begin[b + 1];
     double *out = acc + (int64_t)b * acc_ld + (lo - id_lo);
     // the atomic and the plain variant are both launched; the monotonicity flag picks the one that runs
+    if (use_flag && !*use_flag) return;
     if ((*run_flag != 0) != kAtomic) return;
     if (r_begin == r_end) return;            // acc was zero-filled by the caller
     for (int i = tid; i < width; i += kAcc2Threads) col[i] = 0.0;
@@ -333,6 +354,169 @@ index_accumulate2_kernel(const int32_t *__restrict__ run_flag, const int64_t *__
     for (int i = tid; i < width; i += kAcc2Threads) out[i] = col[i];
 }
 
+// ---- sample-range variant ----------------------------------------------------------------------
+// intropolis lists each row's samples in strictly ascending order (rows that do not are detected and
+// take the variants above).  The sample-id space is cut into P ranges of 2^shift ids, and ONE WARP owns
+// (bucket, range): it walks the bucket's rows in file order and applies, for each row, the contiguous
+// segment of the row that falls in its range -- distinct samples, so lanes never collide within a row,
+// and a __syncwarp() between rows orders the rows.  Every cell therefore still sees its addends in the
+// reference's order (morna.py:376-388: bit-identical doubles), but there is no block barrier, no
+// id_of_sample gather in the loop, and several small CTAs share an SM.
+//   pre-pass  row_segments_kernel: one warp per bucket-sorted row -> the row's P+1 segment offsets,
+//             its start position and +-idf, stored in sorted order (coalesced for the consumer)
+//   main      index_accumulate3_kernel: warp = (bucket, range), slice of 2^shift doubles in shared memory
+constexpr int kAcc3Warps = 4, kAcc3Threads = kAcc3Warps * 32;
+constexpr int kAcc3Group = 8;        // rows whose first 32 pairs are loaded together
+constexpr int kAcc3Unroll = 4;       // 32-pair chunks in flight inside a long segment
+
+struct RowMeta { int64_t pos; double w; };      // first pair of the row, sign * idf
+
+// Pre-pass, one thread per (bucket-sorted row, range boundary): the first position of the row whose
+// sample id reaches the boundary, by binary search -- valid if the row is ascending, which the main
+// kernel verifies on every pair it loads.  Also the row's start position and +-idf, in sorted order.
+__global__ void __launch_bounds__(256)
+row_segments_kernel(const int64_t *__restrict__ row_off, const int8_t *__restrict__ sign,
+                    const double *__restrict__ idf, const int32_t *__restrict__ sample,
+                    const int32_t *__restrict__ rows_by_bucket, const int32_t *__restrict__ bucket_begin, int32_t dim,
+                    int32_t shift, int32_t n_ranges, int32_t *__restrict__ seg, RowMeta *__restrict__ meta) {
+    const int32_t n_pass = bucket_begin[dim];                  // rows under the threshold sort past the last bucket
+    const int64_t total = (int64_t)n_pass * (n_ranges + 1);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / (n_ranges + 1);
+        const int32_t q = (int32_t)(i - r * (n_ranges + 1));
+        const int32_t j = rows_by_bucket[r];
+        const int64_t b = row_off[j];
+        const int32_t n = (int32_t)(row_off[j + 1] - b);
+        if (q == 0) { meta[r].pos = b; meta[r].w = (double)sign[j] * idf[j]; }
+        int32_t lo = 0, hi = n;                                // first p in [0, n] with sample[b + p] >= q << shift
+        if (q == n_ranges) lo = n;
+        else if (q > 0) {
+            const int32_t bound = q << shift;
+            while (lo < hi) {
+                const int32_t mid = (lo + hi) >> 1;
+                if (__ldg(sample + b + mid) < bound) lo = mid + 1; else hi = mid;
+            }
+        }
+        seg[i] = lo;
+    }
+}
+
+struct WarpMeta { double w[32]; int32_t pos[32]; int32_t n[32]; };      // one batch of 32 rows, this warp's range
+
+// One warp = (bucket, sample-id range): the bucket's rows in file order, for each row the pairs whose
+// sample id falls in the range.  Software pipeline: the rows' metadata is fetched one batch of 32 rows
+// ahead, the first 32 pairs of the next group of eight rows are in flight while the current group is
+// applied.  Runs only if rows_ascending_kernel found every passing row strictly ascending (otherwise
+// the binary-searched segments mean nothing and the barrier-per-row variants do the work).
+__global__ void __launch_bounds__(kAcc3Threads)
+index_accumulate3_kernel(const int32_t *__restrict__ not_ascending, const int32_t *__restrict__ sample,
+                         const int32_t *__restrict__ cov, const int32_t *__restrict__ id_of_sample,
+                         const int32_t *__restrict__ bucket_begin, const int32_t *__restrict__ seg,
+                         const RowMeta *__restrict__ meta, int32_t shift, int32_t n_ranges, int32_t max_sample_id,
+                         int32_t id_lo, int32_t id_hi, double *__restrict__ acc, int64_t acc_ld) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (*not_ascending) return;                                // the order-by-barrier variants run instead
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x;
+    const int range = blockIdx.y * kAcc3Warps + warp;
+    if (range >= n_ranges) return;                             // no block-wide barrier below
+    const int32_t width = 1 << shift, range_lo = range << shift;
+    double *slice = reinterpret_cast<double *>(smem_raw) + (size_t)warp * width;
+    WarpMeta *wm = reinterpret_cast<WarpMeta *>(reinterpret_cast<double *>(smem_raw) + (size_t)kAcc3Warps * width) + 2 * warp;
+    const int32_t r_begin = bucket_begin[b], r_end = bucket_begin[b + 1];
+    const int nrows = r_end - r_begin;
+    if (nrows == 0) return;                                    // acc was zero-filled by the caller
+    for (int i = lane; i < width; i += 32) slice[i] = 0.0;
+    const int n_groups = (nrows + kAcc3Group - 1) / kAcc3Group, n_batches = (nrows + 31) / 32;
+    // stage A: this lane's row of a batch -> registers; published to shared memory one batch ahead of use
+    int32_t a_pos = 0, a_n = 0;
+    double a_w = 0.0;
+    auto fetch_meta = [&](int batch) {
+        const int32_t r = r_begin + 32 * batch + lane;
+        a_pos = 0; a_n = 0; a_w = 0.0;
+        if (batch < n_batches && r < r_end) {
+            const int32_t *sg = seg + (int64_t)r * (n_ranges + 1) + range;
+            const int32_t lo = sg[0], hi = sg[1];
+            const RowMeta mt = meta[r];
+            a_pos = (int32_t)mt.pos + lo; a_n = max(hi - lo, 0); a_w = mt.w;    // nnz < 2^31 (checked by the host entry)
+        }
+    };
+    auto publish_meta = [&](int batch) {
+        WarpMeta &m = wm[batch & 1];
+        m.pos[lane] = a_pos; m.n[lane] = a_n; m.w[lane] = a_w;
+        __syncwarp();
+    };
+    // stage B: first 32 pairs of each row of a group, all loads in flight together
+    auto issue = [&](int g, int32_t (&ps)[kAcc3Group], int32_t (&pc)[kAcc3Group]) {
+        if ((g & 3) == 0) {                                    // first group of a batch: its rows' metadata becomes visible,
+            publish_meta(g >> 2);                              // and the next batch's starts to load
+            fetch_meta((g >> 2) + 1);
+        }
+        const WarpMeta &m = wm[(g >> 2) & 1];
+#pragma unroll
+        for (int u = 0; u < kAcc3Group; ++u) {
+            const int t = (g & 3) * kAcc3Group + u;
+            const bool have = lane < m.n[t];
+            const int32_t pos = m.pos[t];
+            ps[u] = have ? __ldg(sample + pos + lane) : -1;
+            pc[u] = have ? __ldg(cov + pos + lane) : 0;
+        }
+    };
+    // stage C: the group's rows applied in file order
+    auto apply = [&](int g, const int32_t (&ps)[kAcc3Group], const int32_t (&pc)[kAcc3Group]) {
+        const WarpMeta &m = wm[(g >> 2) & 1];
+#pragma unroll
+        for (int u = 0; u < kAcc3Group; ++u) {
+            const int t = (g & 3) * kAcc3Group + u;
+            if (g * kAcc3Group + u >= nrows) break;
+            const double w = m.w[t];
+            const int32_t n = m.n[t];
+            if (ps[u] >= 0) {
+                double *cell = slice + (ps[u] - range_lo);
+                *cell = __dadd_rn(*cell, __dmul_rn((double)pc[u], w));          // product rounded, then added: as the reference
+            }
+            if (n > 32) {                                      // long segment: the rest of the row, four chunks at a time
+                const int32_t pos = m.pos[t];
+                for (int32_t c = 32; c < n; c += 32 * kAcc3Unroll) {
+                    int32_t qs[kAcc3Unroll], qc[kAcc3Unroll];
+#pragma unroll
+                    for (int v = 0; v < kAcc3Unroll; ++v) {
+                        const int32_t i = c + 32 * v + lane;
+                        qs[v] = i < n ? __ldg(sample + pos + i) : -1;
+                        qc[v] = i < n ? __ldg(cov + pos + i) : 0;
+                    }
+#pragma unroll
+                    for (int v = 0; v < kAcc3Unroll; ++v)
+                        if (qs[v] >= 0) {
+                            double *cell = slice + (qs[v] - range_lo);
+                            *cell = __dadd_rn(*cell, __dmul_rn((double)qc[v], w));
+                        }
+                }
+            }
+            __syncwarp();                                      // rows are applied in file order
+        }
+    };
+
+    fetch_meta(0);
+    int32_t sa[kAcc3Group], ca[kAcc3Group], sb[kAcc3Group], cb[kAcc3Group];
+    issue(0, sa, ca);                                          // (publishes batch 0, starts batch 1's metadata)
+    for (int g = 0; g < n_groups; g += 2) {
+        if (g + 1 < n_groups) issue(g + 1, sb, cb);            // next group's loads fly during this group's adds
+        apply(g, sa, ca);
+        if (g + 1 >= n_groups) break;
+        if (g + 2 < n_groups) issue(g + 2, sa, ca);
+        apply(g + 1, sb, cb);
+    }
+    // the slice is in sample-id order; the accumulator is indexed by internal id
+    double *out = acc + (int64_t)b * acc_ld;
+    for (int i = lane; i < width; i += 32) {
+        const int32_t s = range_lo + i;
+        if (s > max_sample_id) break;
+        const int32_t id = id_of_sample[s];
+        if (id >= id_lo && id < id_hi) out[id - id_lo] = slice[i];
+    }
+}
+
 // ------------------------------------------------------------------ round + transpose
 __global__ void __launch_bounds__(256)
 round_store_kernel(const double *__restrict__ acc, int64_t acc_ld, int32_t n_ids, int32_t dim,
@@ -373,7 +557,8 @@ static IdsWs ids_ws_layout(int64_t m) {
     return w;
 }
 
-struct AccWs { size_t keys_in, keys_out, vals_in, vals_out, begin, cub, cub_bytes, len, voff, scan, scan_bytes, flag, total; };
+constexpr int kAcc3MaxRanges = 32;
+struct AccWs { size_t keys_in, keys_out, vals_in, vals_out, begin, cub, cub_bytes, len, voff, scan, scan_bytes, flag, seg, meta, total; };
 static AccWs acc_ws_layout(int64_t n_rows, int32_t dim) {
     AccWs w{};
     size_t off = 0;
@@ -392,12 +577,18 @@ static AccWs acc_ws_layout(int64_t n_rows, int32_t dim) {
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int64_t *)nullptr, (int64_t *)nullptr, (int)(n_rows + 1));
     w.scan = off; w.scan_bytes = scan_bytes; off += align_up(scan_bytes, 256);
     w.flag = off; off += 256;
+    w.seg = off; off += align_up((size_t)n_rows * (kAcc3MaxRanges + 1) * 4, 256);
+    w.meta = off; off += align_up((size_t)n_rows * sizeof(RowMeta), 256);
     w.total = off + 256;
     return w;
 }
 
 static int g_acc_pipelined = 1;      // morna_debug_set_tuning key 4
+static int g_acc_split = 1;          // morna_debug_set_tuning key 7: id tiles per bucket column (more CTAs per SM)
+static int g_acc_variant = 3;        // morna_debug_set_tuning key 8: 3 = sample-range warps first, else barrier-per-row only
 void set_acc_pipelined(int v) { g_acc_pipelined = v ? 1 : 0; }
+void set_acc_split(int v) { g_acc_split = v > 0 ? v : 1; }
+void set_acc_variant(int v) { g_acc_variant = v; }
 
 static unsigned grid_for(int64_t work, int threads) {
     int64_t g = (work + threads - 1) / threads;
@@ -494,11 +685,11 @@ extern "C" size_t morna_index_accumulate_workspace_bytes(int64_t n_rows, int32_t
 extern "C" int morna_index_accumulate(const int64_t *row_off, const uint8_t *pass, const int32_t *bucket,
                                       const int8_t *sign, const double *idf, int64_t n_rows,
                                       const int32_t *sample, const int32_t *cov, int64_t nnz,
-                                      const int32_t *id_of_sample, int32_t id_lo, int32_t id_hi, int32_t dim,
-                                      double *acc, int64_t acc_ld, void *workspace, size_t workspace_bytes,
-                                      void *stream) {
+                                      const int32_t *id_of_sample, int32_t max_sample_id, int32_t id_lo, int32_t id_hi,
+                                      int32_t dim, double *acc, int64_t acc_ld, void *workspace,
+                                      size_t workspace_bytes, void *stream) {
     if (!row_off || !pass || !bucket || !sign || !idf || !id_of_sample || !acc || n_rows < 0 || nnz < 0 ||
-        dim <= 0 || id_lo < 0 || id_hi < id_lo || acc_ld < (int64_t)(id_hi - id_lo) || n_rows > 0x7fffffff)
+        max_sample_id < 0 || dim <= 0 || id_lo < 0 || id_hi < id_lo || acc_ld < (int64_t)(id_hi - id_lo) || n_rows > 0x7fffffff)
         return MORNA_ERR_INVALID_ARGUMENT;
     if (nnz > 0 && (!sample || !cov)) return MORNA_ERR_INVALID_ARGUMENT;
     AccWs w = acc_ws_layout(n_rows, dim);
@@ -522,22 +713,47 @@ extern "C" int morna_index_accumulate(const int64_t *row_off, const uint8_t *pas
     bucket_begin_kernel<<<grid_for(n_rows + 1, 256), 256, 0, s>>>(keys_out, n_rows, dim, begin);
     MORNA_LAUNCH_CHECK();
     const int32_t range = id_hi - id_lo;
+    auto *flag = (int32_t *)(ws + w.flag);                 // [0] a row repeats a sample, [1] a row is not ascending
+    MORNA_CUDA_TRY(cudaMemsetAsync(flag, 0, 2 * sizeof(int32_t), s));
+    const int32_t *use_old = nullptr;                      // nullptr: the barrier-per-row variants run unconditionally
+    rows_monotonic_kernel<<<grid_for(n_rows * 32, 256), 256, 0, s>>>(row_off, pass, n_rows, sample, flag);
+    MORNA_LAUNCH_CHECK();
+    // few rows per bucket (very wide --features): the per-(bucket, range) set-up of the warp variant is not
+    // amortised and the barrier-per-row variants are faster (measured: 30,000 features over 1.1 M rows)
+    const bool enough_rows = g_acc_variant == 4 || n_rows / dim >= 64 || n_rows < 4096;
+    if ((g_acc_variant == 3 || g_acc_variant == 4) && enough_rows && nnz < 0x7fffffff) {
+        // sample-id ranges of 2^shift ids, at most kAcc3MaxRanges of them, at least 1024 ids wide
+        int32_t shift = 10;
+        while (((int64_t)max_sample_id >> shift) + 1 > kAcc3MaxRanges) ++shift;
+        const int32_t n_ranges = (int32_t)(((int64_t)max_sample_id >> shift) + 1);
+        auto *seg = (int32_t *)(ws + w.seg);
+        auto *meta = (RowMeta *)(ws + w.meta);
+        row_segments_kernel<<<grid_for(n_rows * (n_ranges + 1), 256), 256, 0, s>>>(row_off, sign, idf, sample, vals_out, begin,
+                                                                                 dim, shift, n_ranges, seg, meta);
+        MORNA_LAUNCH_CHECK();
+        const size_t smem3 = (size_t)kAcc3Warps * (((size_t)1 << shift) * sizeof(double) + 2 * sizeof(WarpMeta));
+        if (smem3 <= 200 * 1024) {
+            MORNA_CUDA_TRY(cudaFuncSetAttribute(index_accumulate3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            dim3 grid3((unsigned)dim, (unsigned)((n_ranges + kAcc3Warps - 1) / kAcc3Warps));
+            index_accumulate3_kernel<<<grid3, kAcc3Threads, smem3, s>>>(flag + 1, sample, cov, id_of_sample, begin, seg, meta, shift,
+                                                                      n_ranges, max_sample_id, id_lo, id_hi, acc, acc_ld);
+            MORNA_LAUNCH_CHECK();
+            use_old = flag + 1;                            // the variants below run only if a row was not ascending
+        }
+    }
     if (g_acc_pipelined) {
         auto *len = (int64_t *)(ws + w.len);
         auto *voff = (int64_t *)(ws + w.voff);
         MORNA_CUDA_TRY(cudaMemsetAsync(len + n_rows, 0, sizeof(int64_t), s));
-        sorted_row_len_kernel<<<grid_for(n_rows, 256), 256, 0, s>>>(row_off, vals_out, n_rows, len);
+        sorted_row_len_kernel<<<grid_for(n_rows, 256), 256, 0, s>>>(use_old, row_off, vals_out, n_rows, len);
         MORNA_LAUNCH_CHECK();
         size_t scan_bytes = w.scan_bytes;
         MORNA_CUDA_TRY(cub::DeviceScan::ExclusiveSum(ws + w.scan, scan_bytes, len, voff, (int)(n_rows + 1), s));
         count_launch(2);
-        const int32_t tile2 = range < kAcc2Tile ? range : kAcc2Tile;
+        int32_t tile2 = range < kAcc2Tile ? range : kAcc2Tile;
+        if (g_acc_split > 1) { const int32_t t = (range + g_acc_split - 1) / g_acc_split; if (t < tile2) tile2 = t; }
         const int32_t tiles2 = (range + tile2 - 1) / tile2;
         const size_t smem2 = (size_t)tile2 * sizeof(double) + kAcc2MetaBytes;
-        auto *flag = (int32_t *)(ws + w.flag);
-        MORNA_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int32_t), s));
-        rows_monotonic_kernel<<<grid_for(n_rows * 32, 256), 256, 0, s>>>(row_off, pass, n_rows, sample, flag);
-        MORNA_LAUNCH_CHECK();
         if (smem2 > 48 * 1024) {
             MORNA_CUDA_TRY(cudaFuncSetAttribute(index_accumulate2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)(kAcc2Tile * sizeof(double) + kAcc2MetaBytes)));
@@ -545,10 +761,10 @@ extern "C" int morna_index_accumulate(const int64_t *row_off, const uint8_t *pas
                                                 (int)(kAcc2Tile * sizeof(double) + kAcc2MetaBytes)));
         }
         dim3 grid2((unsigned)dim, (unsigned)tiles2);
-        index_accumulate2_kernel<false><<<grid2, kAcc2Threads, smem2, s>>>(flag, row_off, sign, idf, sample, cov, id_of_sample,
+        index_accumulate2_kernel<false><<<grid2, kAcc2Threads, smem2, s>>>(use_old, flag, row_off, sign, idf, sample, cov, id_of_sample,
                                                                          vals_out, begin, voff, id_lo, id_hi, tile2, acc, acc_ld);
         MORNA_LAUNCH_CHECK();
-        index_accumulate2_kernel<true><<<grid2, kAcc2Threads, smem2, s>>>(flag, row_off, sign, idf, sample, cov, id_of_sample,
+        index_accumulate2_kernel<true><<<grid2, kAcc2Threads, smem2, s>>>(use_old, flag, row_off, sign, idf, sample, cov, id_of_sample,
                                                                         vals_out, begin, voff, id_lo, id_hi, tile2, acc, acc_ld);
         MORNA_LAUNCH_CHECK();
         return MORNA_OK;
@@ -560,7 +776,7 @@ extern "C" int morna_index_accumulate(const int64_t *row_off, const uint8_t *pas
         MORNA_CUDA_TRY(cudaFuncSetAttribute(index_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(kAccTile * sizeof(double))));
     dim3 grid((unsigned)dim, (unsigned)tiles);
-    index_accumulate_kernel<<<grid, kAccThreads, smem, s>>>(row_off, sign, idf, sample, cov, id_of_sample, vals_out,
+    index_accumulate_kernel<<<grid, kAccThreads, smem, s>>>(use_old, row_off, sign, idf, sample, cov, id_of_sample, vals_out,
                                                           begin, id_lo, id_hi, tile, acc, acc_ld);
     MORNA_LAUNCH_CHECK();
     return MORNA_OK;

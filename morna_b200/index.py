@@ -136,7 +136,7 @@ class MornaIndex(object):
             _lib.check(lib.morna_index_accumulate(
                 _lib.dev_ptr(d_row_off), _lib.dev_ptr(d_pass), _lib.dev_ptr(d_bucket), _lib.dev_ptr(d_sign),
                 _lib.dev_ptr(d_idf), n_rows, _lib.dev_ptr(d_sample), _lib.dev_ptr(d_cov), nnz,
-                _lib.dev_ptr(d_id_of), lo, hi, self.dim, _lib.dev_ptr(d_acc), acc_ld,
+                _lib.dev_ptr(d_id_of), max_sample_id, lo, hi, self.dim, _lib.dev_ptr(d_acc), acc_ld,
                 _lib.dev_ptr(ws), ws.numel(), sp), "morna_index_accumulate")
             self.vectors = torch.empty((width, self.ld), dtype=torch.float32, device=dev)
             _lib.check(lib.morna_round_store(_lib.dev_ptr(d_acc), acc_ld, width, self.dim,

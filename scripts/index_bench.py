@@ -14,6 +14,7 @@ ap.add_argument("--samples", type=int, default=21504)
 ap.add_argument("--dims", type=str, default="500,1000,3000,10000,30000")
 ap.add_argument("--threshold", type=int, default=100)
 ap.add_argument("--cpu-pairs", type=float, default=5e6)
+ap.add_argument("--splits", type=str, default="", help="sweep morna_debug_set_tuning key 7 (id tiles per bucket column)")
 args = ap.parse_args()
 lib = _lib.load()
 dev = torch.device("cuda")
@@ -85,8 +86,15 @@ for dim in [int(x) for x in args.dims.split(",")]:
     acc_ld = (n_kept + 31) // 32 * 32
     d_acc = torch.empty(dim * acc_ld, dtype=torch.float64, device=dev)
     ws_acc = _lib.workspace(lib.morna_index_accumulate_workspace_bytes(J, dim), dev)
+    for split in [int(x) for x in args.splits.split(",") if x]:
+        lib.morna_debug_set_tuning(7, split)
+        t_s = timed(lambda: _lib.check(lib.morna_index_accumulate(_lib.dev_ptr(d_row_off), _lib.dev_ptr(d_pass), _lib.dev_ptr(d_bucket), _lib.dev_ptr(d_sign),
+                    _lib.dev_ptr(d_idf), J, _lib.dev_ptr(d_sample), _lib.dev_ptr(d_cov), nnz, _lib.dev_ptr(d_id_of), N, 0, n_kept, dim, _lib.dev_ptr(d_acc),
+                    acc_ld, _lib.dev_ptr(ws_acc), ws_acc.numel(), sp), "acc"), reps=2)
+        print("D=%5d: id tiles per column %d -> accumulate %.2f ms" % (dim, split, t_s), flush=True)
+        lib.morna_debug_set_tuning(7, 1)
     t_acc = timed(lambda: _lib.check(lib.morna_index_accumulate(_lib.dev_ptr(d_row_off), _lib.dev_ptr(d_pass), _lib.dev_ptr(d_bucket), _lib.dev_ptr(d_sign),
-                  _lib.dev_ptr(d_idf), J, _lib.dev_ptr(d_sample), _lib.dev_ptr(d_cov), nnz, _lib.dev_ptr(d_id_of), 0, n_kept, dim, _lib.dev_ptr(d_acc),
+                  _lib.dev_ptr(d_idf), J, _lib.dev_ptr(d_sample), _lib.dev_ptr(d_cov), nnz, _lib.dev_ptr(d_id_of), N, 0, n_kept, dim, _lib.dev_ptr(d_acc),
                   acc_ld, _lib.dev_ptr(ws_acc), ws_acc.numel(), sp), "acc"), reps=2)
     ld = (dim + 3) // 4 * 4
     d_vec = torch.empty((n_kept, ld), dtype=torch.float32, device=dev)
