@@ -308,16 +308,26 @@ def dominant_kernel_roofline(torch, lib, _lib, srch, queries64, peaks):
     flops = 2.0 * nq * rows * srch.dim
     achieved = flops / (ms / 1e3) / 1e12
     peak = peaks["bf16_tflops"]
-    traffic = None
+    traffic = rr_traffic = None
     prof = os.path.join(ROOT, "profiles", "r01_step_summary.json")     # dram bytes per launch from the committed ncu capture
     if os.path.exists(prof):
         with open(prof) as fh:
-            traffic = json.load(fh).get("knn_gemm2_filter_dram_bytes")
+            summary = json.load(fh)
+        traffic, rr_traffic = summary.get("knn_gemm2_filter_dram_bytes"), summary.get("rerank_dist_dram_bytes")
+    # second kernel of the step by time: the exact FP64 re-rank, an HBM/L2 gather of candidates*4*ld bytes per query
+    rr_bytes = float(srch.last_stats[2]) * srch.ld * 4
+    rr_gbs = rr_bytes / (acc[5] / 1e3) / 1e9
+    rerank = {"bound": "hbm", "kernel": "rerank_dist_kernel<8> + rerank_order_kernel (FP64 canonical sums over the candidate rows)",
+              "achieved": rr_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": rr_gbs / peaks["hbm_gbs"],
+              "traffic": rr_traffic, "launch_ms": acc[5],
+              "algorithmic": "candidates * 4 * ld bytes gathered per batch (%d candidates x %d B); rows re-ranked by several "
+                             "queries hit in L2, so achieved can exceed the DRAM traffic rate" % (srch.last_stats[2], srch.ld * 4)}
     return {"bound": "tensor", "kernel": "knn_gemm2_kernel<4> (tcgen05 cta_group::2 fp16 UMMA, filter pass over %d rows)" % rows,
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
             "algorithmic": "2*Q*N*D flops per launch, Q=%d N=%d D=%d" % (nq, rows, srch.dim),
             "launch_ms": ms, "peak_source": peaks["source"] + " bf16 burst (fp16 runs on the same kind::f16 pipe)",
             "phase_ms": {name: round(v, 4) for name, v in zip(PHASE_NAMES, acc)},
+            "second_kernel": rerank,
             "candidates_per_query": {"first_pass": srch.last_stats[1] / nq, "reranked": srch.last_stats[2] / nq,
                                      "overflowed_queries": srch.last_stats[0]},
             "dtype": "fp16 first pass (fp32 accumulate), f64 re-rank"}

@@ -70,9 +70,9 @@ def full(src, dst_prefix):
     if gemm:
         big = max(gemm, key=lambda r: float(r["gpu__time_duration.sum"].split()[0]))
         summary["knn_gemm2_filter_dram_bytes"] = big["dram_bytes_per_launch"]
-    rr = [r for r in out if "rerank_select" in r["kernel"]]
+    rr = [r for r in out if "rerank_dist" in r["kernel"]]
     if rr:
-        summary["rerank_select_dram_bytes"] = rr[0]["dram_bytes_per_launch"]
+        summary["rerank_dist_dram_bytes"] = rr[0]["dram_bytes_per_launch"]
     with open(dst_prefix + ".json", "w") as fh:
         json.dump(summary, fh, indent=1)
     print(open(dst_prefix + ".md").read())
