@@ -299,7 +299,8 @@ def dominant_kernel_roofline(torch, lib, _lib, srch, queries64, peaks):
         torch.cuda.synchronize()
         for i in range(6):
             acc[i] += events[i].elapsed_time(events[i + 1]) / reps
-    n = srch.row_hi - srch.row_lo
+    n_all = srch.row_hi - srch.row_lo
+    n = n_all - (n_all - 1) // srch.BATCH_BLOCK_ROWS * srch.BATCH_BLOCK_ROWS     # the phase events time the last row block
     nq = queries64.shape[0]
     n0 = min(n, 8192)
     ld_h = srch.ld_h
@@ -310,18 +311,19 @@ def dominant_kernel_roofline(torch, lib, _lib, srch, queries64, peaks):
     peak = peaks["bf16_tflops"]
     traffic = rr_traffic = None
     prof = os.path.join(ROOT, "profiles", "r01_step_summary.json")     # dram bytes per launch from the committed ncu capture
-    if os.path.exists(prof):
+    if os.path.exists(prof) and n_all == N_SAMPLES and nq == N_QUERIES:          # the capture was taken at the headline shape
         with open(prof) as fh:
             summary = json.load(fh)
         traffic, rr_traffic = summary.get("knn_gemm2_filter_dram_bytes"), summary.get("rerank_dist_dram_bytes")
     # second kernel of the step by time: the exact FP64 re-rank, an HBM/L2 gather of candidates*4*ld bytes per query
-    rr_bytes = float(srch.last_stats[2]) * srch.ld * 4
+    blocks = (n_all + srch.BATCH_BLOCK_ROWS - 1) // srch.BATCH_BLOCK_ROWS
+    rr_bytes = float(srch.last_stats[2]) / blocks * srch.ld * 4                  # (candidates of one row block)
     rr_gbs = rr_bytes / (acc[5] / 1e3) / 1e9
     rerank = {"bound": "hbm", "kernel": "rerank_dist_kernel<8> + rerank_order_kernel (FP64 canonical sums over the candidate rows)",
               "achieved": rr_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": rr_gbs / peaks["hbm_gbs"],
               "traffic": rr_traffic, "launch_ms": acc[5],
               "algorithmic": "candidates * 4 * ld bytes gathered per batch (%d candidates x %d B); rows re-ranked by several "
-                             "queries hit in L2, so achieved can exceed the DRAM traffic rate" % (srch.last_stats[2], srch.ld * 4)}
+                             "queries hit in L2, so achieved can exceed the DRAM traffic rate" % (srch.last_stats[2] // blocks, srch.ld * 4)}
     return {"bound": "tensor", "kernel": "knn_gemm2_kernel<4> (tcgen05 cta_group::2 fp16 UMMA, filter pass over %d rows)" % rows,
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
             "algorithmic": "2*Q*N*D flops per launch, Q=%d N=%d D=%d" % (nq, rows, srch.dim),

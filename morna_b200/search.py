@@ -278,7 +278,10 @@ class MornaSearch(object):
         results as ``exact_search_batch`` per batch.  ``depth`` batches are in flight, each on its own
         CUDA stream with its own pinned staging buffers and workspace, so batch i+1's host->device
         copy and batch i-1's device->host copy overlap batch i's kernels."""
-        pipe = BatchPipeline(self, k, depth)
+        pipes = self.__dict__.setdefault("_pipes", {})
+        pipe = pipes.get((k, depth))           # slots (streams, pinned buffers, workspaces) are kept between calls
+        if pipe is None or pipe.head != pipe.tail:
+            pipe = pipes[(k, depth)] = BatchPipeline(self, k, depth)
         pending = 0
         for q in batches:
             if pending == depth:
@@ -373,15 +376,17 @@ class BatchPipeline(object):
             sl.stream = torch.cuda.Stream(device=search.device)
             sl.done = torch.cuda.Event()
             sl.nq = -1
+            sl.host_q = None
             self.slots.append(sl)
         self.head = self.tail = 0           # next slot to submit into / to collect from
 
-    def _size(self, sl, nq, dtype):
+    def _size(self, sl, nq, dtype, staging):
         s, k = self.search, self.k
-        if sl.nq == nq and sl.host_q.dtype == dtype:
+        if staging and (sl.host_q is None or sl.host_q.shape[0] != nq or sl.host_q.dtype != dtype):
+            sl.host_q = torch.empty((nq, s.dim), dtype=dtype).pin_memory()      # page-locking is slow: only when needed
+        if sl.nq == nq:
             return
         sl.nq = nq
-        sl.host_q = torch.empty((nq, s.dim), dtype=dtype).pin_memory()
         sl.host_ids = torch.empty((nq, k), dtype=torch.int32).pin_memory()
         sl.host_d = torch.empty((nq, k), dtype=torch.float64).pin_memory()
         sl.host_stats = torch.empty((1 + (s.row_hi - s.row_lo - 1) // s.BATCH_BLOCK_ROWS, 4), dtype=torch.int32).pin_memory()
@@ -394,8 +399,9 @@ class BatchPipeline(object):
         q = torch.from_numpy(np.ascontiguousarray(queries)) if isinstance(queries, np.ndarray) else queries
         if q.dtype != torch.float32:
             q = q.to(torch.float64)
-        self._size(sl, q.shape[0], q.dtype)
-        if q.is_pinned() and q.is_contiguous():
+        direct = q.is_pinned() and q.is_contiguous()
+        self._size(sl, q.shape[0], q.dtype, staging=not direct)
+        if direct:
             src = q                          # already page-locked: copied straight from the caller's buffer,
         else:                                # which must stay untouched until collect()
             sl.host_q.copy_(q)               # pageable source -> the slot's pinned staging buffer
