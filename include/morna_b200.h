@@ -86,6 +86,24 @@ int morna_assign_internal_ids(const int64_t *row_off, const uint8_t *pass, int64
                               int32_t *id_of_sample, int32_t *n_kept,
                               void *workspace, size_t workspace_bytes, void *stream);
 
+/* Host tokenizer (no GPU): intropolis text rows -> the binary CSR the kernels stream.  Replaces the
+ * per-row Python of go_index's loop (morna.py:848-853): key = first three tab-separated fields joined
+ * by single spaces, samples / coverages = comma lists of the last two fields, zip() -> min length.
+ * `text` holds whole '\n'-separated lines.  Rows that are not plainly canonical (leading/trailing
+ * whitespace, fewer than five fields, lists of unequal length, anything but unsigned decimal integers
+ * without leading zeros)
+ * get needs_python[row] = 1 and an empty entry: the caller re-tokenises them with the reference's
+ * str.strip/str.split/int() semantics, so results never differ from the reference's.
+ *   morna_tokenize_count: sizes for the caller's allocations (rows, key bytes, pairs)
+ *   morna_tokenize_fill:  keys [key_bytes], key_off int32[rows+1], row_off int64[rows+1], sample/cov
+ *                         int32[pairs], line_off int64[rows+1] (byte offset of each line in text),
+ *                         needs_python uint8[rows].  All host memory. */
+int morna_tokenize_count(const char *text, size_t nbytes, int32_t n_threads, int64_t *n_rows,
+                         int64_t *key_bytes, int64_t *n_pairs);
+int morna_tokenize_fill(const char *text, size_t nbytes, int32_t n_threads, uint8_t *keys, int32_t *key_off,
+                        int64_t *row_off, int32_t *sample, int32_t *cov, int64_t *line_off,
+                        uint8_t *needs_python);
+
 /* Scatter-add of sign * (coverage * idf) into per-sample vectors.  Replaces the
  * per-pair loop at morna.py:376-388.  Sums are double and every (sample, bucket)
  * cell is accumulated in file row order, so cells equal the reference's Python

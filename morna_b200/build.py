@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmorna_b200.so")
-SOURCES = ["api.cu", "index_build.cu", "search_exact.cu", "search_single.cu", "search_batched.cu"]
+SOURCES = ["api.cu", "index_build.cu", "search_exact.cu", "search_single.cu", "search_batched.cu", "tokenize.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("MORNA_NVCC_EXTRA", "").split()
 
@@ -34,7 +34,7 @@ def build(force=False, verbose=False):
     objs = []
     logs = []
     for src in SOURCES:
-        obj = os.path.join(CSRC, src[:-3] + ".o")
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
         cmd = [nvcc_path()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
         p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         logs.append(p.stdout)
@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(p.stdout)
             raise RuntimeError("nvcc failed on " + src)
         objs.append(obj)
-    cmd = [nvcc_path(), "-shared", "-o", OUT] + objs + ["-lcudart"]
+    cmd = [nvcc_path(), "-shared", "-o", OUT] + objs + ["-lcudart", "-lpthread"]
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if p.returncode != 0:
         sys.stderr.write(p.stdout)

@@ -78,6 +78,59 @@ class MornaIndex(object):
                 out.flush()
             self.add_junction(*tokenize_line(line))
 
+    def add_text(self, buf, seen_samples=None, n_threads=None):
+        """The same row loop over a bytes block of whole lines, tokenised natively
+        (csrc/tokenize.cpp): the threshold test and the cumulative frequency stay here
+        (morna.py:361-365), rows go to the CSR store in bulk.  Rows the native tokenizer does not
+        take (anything not plainly canonical) go through ``tokenize_line`` in their place.
+        ``seen_samples``: optional set updated with the distinct sample-id strings of every row
+        (count_samples, morna.py:809-822) so one pass over the file serves both."""
+        from . import parse
+        keys, key_off, row_off, sample, cov, line_off, needs = parse.tokenize_buffer(buf, n_threads)
+        n = len(needs)
+        odd = np.nonzero(needs)[0].tolist()
+        start = 0
+        for stop in odd + [n]:
+            if stop > start:
+                self._add_block(keys, key_off, row_off, sample, cov, start, stop, seen_samples)
+            if stop < n:
+                line = bytes(buf[line_off[stop]:line_off[stop + 1]]).decode("utf-8")
+                if seen_samples is not None:
+                    seen_samples.update(line.split("\t")[-2].split(","))
+                self.add_junction(*parse.tokenize_line(line))
+            start = stop + 1
+
+    def _add_block(self, keys, key_off, row_off, sample, cov, r0, r1, seen_samples):
+        lens = np.diff(row_off[r0:r1 + 1])
+        passing = lens >= self.sample_threshold
+        running = np.zeros(r1 - r0, dtype=np.int64)
+        kbytes = keys.tobytes()
+        freqs = self.sample_frequencies
+        for i in np.nonzero(passing)[0].tolist():        # one dict update per passing row (morna.py:365)
+            key = kbytes[key_off[r0 + i]:key_off[r0 + i + 1]].decode("utf-8")
+            freq = freqs.get(key, 0) + int(lens[i])
+            freqs[key] = freq
+            running[i] = freq
+        self.junc_id += r1 - r0
+        self.skipped += int((~passing).sum())
+        p0, p1 = int(row_off[r0]), int(row_off[r1])
+        if seen_samples is not None and p1 > p0:         # canonical integers: distinct strings == distinct values
+            seen_samples.update(np.unique(sample[p0:p1]).astype(str).tolist())
+        if self._store_skipped or passing.all():
+            keep = slice(None)
+            self._rows.add_block(keys[key_off[r0]:key_off[r1]], np.diff(key_off[r0:r1 + 1]), lens, sample[p0:p1], cov[p0:p1])
+            self._pass.extend(passing.astype(np.uint8).tolist())
+            self._running_freq.extend(running.tolist())
+        else:                                            # rows under the threshold are not shipped
+            rows = np.nonzero(passing)[0]
+            pair_mask = np.repeat(passing, lens)
+            key_lens = np.diff(key_off[r0:r1 + 1])
+            key_mask = np.repeat(passing, key_lens)
+            self._rows.add_block(keys[key_off[r0]:key_off[r1]][key_mask], key_lens[rows], lens[rows],
+                                 sample[p0:p1][pair_mask], cov[p0:p1][pair_mask])
+            self._pass.extend([1] * len(rows))
+            self._running_freq.extend(running[rows].tolist())
+
     # ------------------------------------------------------------------ device build
     def build(self, n_trees=None, verbose=False, id_range=None, stream=None):
         """Runs the device pipeline.  ``n_trees`` is accepted for signature parity and
@@ -184,17 +237,23 @@ def go_index(intropolis, basename, features, n_trees, sample_count, sample_thres
              verbose, metafile, out=None):
     """morna.py:824-865."""
     import sys
-    from .parse import count_samples, open_intropolis
     out = out or sys.stdout
-    if not sample_count:
-        with open_intropolis(intropolis) as fh:
-            sample_count = count_samples(fh, verbose, out)
-    if verbose:
-        out.write("\nThere are %d samples.\n" % sample_count)
-    index = MornaIndex(sample_count, basename, dim=features, sample_threshold=sample_threshold,
+    from . import parse
+    seen = None if sample_count else set()              # one pass serves count_samples too (morna.py:789-822)
+    index = MornaIndex(sample_count or 0, basename, dim=features, sample_threshold=sample_threshold,
                        metafile=metafile, buffer_size=buffer_size)
-    with open_intropolis(intropolis) as fh:
-        index.add_lines(fh, verbose=verbose, out=out)
+    done = 0
+    with parse.open_intropolis_binary(intropolis) as fh:
+        for block in parse.read_blocks(fh):
+            index.add_text(block, seen_samples=seen)
+            if verbose:
+                done += block.count(b"\n")
+                out.write("%d lines into index making\r" % done)
+                out.flush()
+    if seen is not None:
+        index.sample_count = len(seen)
+    if verbose:
+        out.write("\nThere are %d samples.\n" % index.sample_count)
     if verbose:
         out.write("Finished making index; now building\n")
     index.build(n_trees, verbose=verbose)

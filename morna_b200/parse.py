@@ -38,36 +38,107 @@ def count_samples(lines, verbose=False, out=None):
 
 
 class RowBatch(object):
-    """Pre-tokenised rows in the binary CSR form the kernels stream:
-    packed key bytes + int32 offsets, int64 pair offsets, int32 samples / coverages."""
+    """Pre-tokenised rows in the binary CSR form the kernels stream: packed key bytes + int32 offsets,
+    int64 pair offsets, int32 samples / coverages.  Rows arrive one at a time (``add``) or as whole
+    tokenised blocks (``add_block``); ``finish`` concatenates in arrival order."""
 
     def __init__(self):
-        self.keys = []            # list of bytes
-        self.lens = []            # pairs per row
-        self.samples = []         # list of int32 arrays
-        self.coverages = []
+        self.key_chunks = []      # bytes / uint8 arrays
+        self.keylen_chunks = []   # int64 arrays: key length per row
+        self.len_chunks = []      # int64 arrays: pairs per row
+        self.sample_chunks = []   # int32 arrays
+        self.cov_chunks = []
+        self.n_rows = 0
 
     def add(self, key, samples, coverages):
         n = min(len(samples), len(coverages))        # zip() semantics, morna.py:376
-        self.keys.append(key.encode("utf-8") if isinstance(key, str) else bytes(key))
-        self.lens.append(n)
-        self.samples.append(np.asarray(samples[:n], dtype=np.int32))
-        self.coverages.append(np.asarray(coverages[:n], dtype=np.int32))
+        kb = key.encode("utf-8") if isinstance(key, str) else bytes(key)
+        self.key_chunks.append(np.frombuffer(kb, dtype=np.uint8))
+        self.keylen_chunks.append(np.array([len(kb)], dtype=np.int64))
+        self.len_chunks.append(np.array([n], dtype=np.int64))
+        self.sample_chunks.append(np.asarray(samples[:n], dtype=np.int32))
+        self.cov_chunks.append(np.asarray(coverages[:n], dtype=np.int32))
+        self.n_rows += 1
+
+    def add_block(self, packed_keys, key_lens, pair_lens, samples, coverages):
+        """Rows of one tokenised block, already concatenated (arrays are kept, not copied)."""
+        self.key_chunks.append(packed_keys)
+        self.keylen_chunks.append(np.asarray(key_lens, dtype=np.int64))
+        self.len_chunks.append(np.asarray(pair_lens, dtype=np.int64))
+        self.sample_chunks.append(samples)
+        self.cov_chunks.append(coverages)
+        self.n_rows += len(key_lens)
 
     def __len__(self):
-        return len(self.keys)
+        return self.n_rows
 
     def finish(self):
-        n_rows = len(self.keys)
-        key_off = np.zeros(n_rows + 1, dtype=np.int32)
+        n_rows = self.n_rows
+        cat = lambda parts, dt: (np.concatenate(parts) if parts else np.zeros(0, dt)).astype(dt, copy=False)
+        key_off = np.zeros(n_rows + 1, dtype=np.int64)
         if n_rows:
-            key_off[1:] = np.cumsum([len(k) for k in self.keys])
-        packed = np.frombuffer(b"".join(self.keys), dtype=np.uint8).copy() if n_rows else np.zeros(0, np.uint8)
+            key_off[1:] = np.cumsum(cat(self.keylen_chunks, np.int64))
+        if key_off[-1] > 0x7fffffff:
+            raise ValueError("junction keys exceed 2 GiB")
+        packed = cat(self.key_chunks, np.uint8)
         row_off = np.zeros(n_rows + 1, dtype=np.int64)
         if n_rows:
-            row_off[1:] = np.cumsum(self.lens, dtype=np.int64)
-        cat = lambda parts: (np.concatenate(parts) if parts else np.zeros(0, np.int32)).astype(np.int32, copy=False)
-        return packed, key_off, row_off, cat(self.samples), cat(self.coverages)
+            row_off[1:] = np.cumsum(cat(self.len_chunks, np.int64))
+        return (packed, key_off.astype(np.int32), row_off, cat(self.sample_chunks, np.int32),
+                cat(self.cov_chunks, np.int32))
+
+
+def tokenize_buffer(buf, n_threads=None):
+    """Native tokenizer (morna_b200/csrc/tokenize.cpp) over a bytes object holding whole lines.
+    Returns (packed_keys u8, key_off i32[n+1], row_off i64[n+1], sample i32, cov i32, line_off i64[n+1],
+    needs_python u8[n]); rows with needs_python set are empty and must go through ``tokenize_line``."""
+    import ctypes
+    import os
+    from . import _lib
+    lib = _lib.load()
+    if n_threads is None:
+        n_threads = max(1, min(32, os.cpu_count() or 1))
+    n = ctypes.c_int64()
+    kb = ctypes.c_int64()
+    pr = ctypes.c_int64()
+    nbytes = len(buf)
+    _lib.check(lib.morna_tokenize_count(buf, nbytes, n_threads, ctypes.byref(n), ctypes.byref(kb), ctypes.byref(pr)),
+               "morna_tokenize_count")
+    n, kb, pr = n.value, kb.value, pr.value
+    keys = np.empty(max(kb, 1), dtype=np.uint8)
+    key_off = np.empty(n + 1, dtype=np.int32)
+    row_off = np.empty(n + 1, dtype=np.int64)
+    sample = np.empty(max(pr, 1), dtype=np.int32)
+    cov = np.empty(max(pr, 1), dtype=np.int32)
+    line_off = np.empty(n + 1, dtype=np.int64)
+    needs = np.empty(max(n, 1), dtype=np.uint8)
+    _lib.check(lib.morna_tokenize_fill(buf, nbytes, n_threads, keys.ctypes.data, key_off.ctypes.data, row_off.ctypes.data,
+                                       sample.ctypes.data, cov.ctypes.data, line_off.ctypes.data, needs.ctypes.data),
+               "morna_tokenize_fill")
+    return keys[:kb], key_off, row_off, sample[:pr], cov[:pr], line_off, needs[:n]
+
+
+def read_blocks(fh, block_bytes=64 << 20):
+    """Binary file object -> bytes blocks ending at a line boundary."""
+    tail = b""
+    while True:
+        chunk = fh.read(block_bytes)
+        if not chunk:
+            if tail:
+                yield tail
+            return
+        cut = chunk.rfind(b"\n")
+        if cut < 0:
+            tail += chunk
+            continue
+        yield tail + chunk[:cut + 1]
+        tail = chunk[cut + 1:]
+
+
+def open_intropolis_binary(path):
+    with open(path, "rb") as probe:
+        magic = probe.read(2)
+    return gzip.open(path, "rb") if magic == b"\x1f\x8b" else open(path, "rb")
 
 
 # ---------------------------------------------------------------- query streams

@@ -407,3 +407,38 @@ def test_single_query_ties_fall_back_and_shard_offsets():
     qg = torch.from_numpy(G[900].astype(np.float64)).cuda()
     p_ids, p_d = part.single_search_device(qg, 10)
     assert int(p_ids[0, 0]) == 900 and p_ids.min() >= 501
+
+
+# ------------------------------------------------------------------ native tokenizer feeding the index build
+def test_index_from_text_blocks_equals_index_from_python_rows(tmp_path):
+    import gzip
+    from morna_b200 import parse
+    from morna_b200.index import MornaIndex, go_index
+    rng = np.random.default_rng(77)
+    lines = synthetic_rows(rng, 500, 3000)
+    lines.insert(40, " chr7\t5\t9\t+\tGT\tAG\t7,30,90\t2,4,1\n")                    # leading blank: Python's strip()
+    lines.insert(90, "chr7\t50\t90\t+\tGT\tAG\t5,9,20,77,78,79\t1,1,1,1\n")           # unequal lists: zip()
+    lines.insert(91, "chr7\t51\t91\t+\tGT\tAG\t1,2,3,4,05\t1,1,1,1,1\n")              # "05": its own count_samples string
+    text = "".join(lines).encode()
+    n_samples = parse.count_samples(lines)
+    a = MornaIndex(n_samples, "unused", dim=200, sample_threshold=4)
+    a.add_lines(lines)
+    a.build()
+    for block_bytes in (1 << 30, 5000):
+        seen = set()
+        b = MornaIndex(0, "unused", dim=200, sample_threshold=4)
+        for block in parse.read_blocks(io.BytesIO(text), block_bytes=block_bytes):
+            b.add_text(block, seen_samples=seen, n_threads=3)
+        assert len(seen) == n_samples
+        b.sample_count = len(seen)
+        b.build()
+        assert b.internal_id_map == a.internal_id_map and b.skipped == a.skipped and b.junc_id == a.junc_id
+        assert b.sample_frequencies == a.sample_frequencies
+        assert np.array_equal(b.matrix_f32(), a.matrix_f32())
+    # and through the command's own entry point, gzipped, sample count discovered in the same pass
+    path = str(tmp_path / "rows.tsv.gz")
+    with gzip.open(path, "wb") as fh:
+        fh.write(text)
+    c = go_index(path, str(tmp_path / "idx"), 200, None, None, 4, 1024, False, None, out=io.StringIO())
+    assert c.sample_count == n_samples
+    assert np.array_equal(c.matrix_f32(), a.matrix_f32())

@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 from morna_b200 import _lib, cli, files, parse
+from tests.helpers import GOLDEN
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -130,3 +131,78 @@ def test_cli_parser_defaults_match_reference():
     out = io.StringIO()
     cli.results_output(([3, 1], [0.0, 1.4142135623730951]), out)
     assert out.getvalue() == "1.\t3\t0.0\n2.\t1\t1.41421356237\n"
+
+
+# ------------------------------------------------------------------ native tokenizer (host code of the .so, no GPU)
+def _python_rows(text):
+    from morna_b200 import parse
+    return [parse.tokenize_line(line) for line in text.decode().split("\n") if line != ""]
+
+
+def _native_rows(text, n_threads):
+    from morna_b200 import parse
+    keys, key_off, row_off, sample, cov, line_off, needs = parse.tokenize_buffer(text, n_threads)
+    rows = []
+    kb = keys.tobytes()
+    for r in range(len(needs)):
+        line = text[line_off[r]:line_off[r + 1]]
+        if needs[r]:
+            assert row_off[r + 1] == row_off[r] and key_off[r + 1] == key_off[r]
+            rows.append(("python", line))
+        else:
+            rows.append((kb[key_off[r]:key_off[r + 1]].decode(), sample[row_off[r]:row_off[r + 1]].tolist(),
+                         cov[row_off[r]:row_off[r + 1]].tolist()))
+    return rows
+
+
+@pytest.mark.parametrize("n_threads", [1, 3, 16])
+def test_native_tokenizer_matches_python_on_the_reference_fixture(n_threads):
+    text = open(os.path.join(GOLDEN, "tiny_intropolis.tsv"), "rb").read()
+    want = _python_rows(text)
+    got = _native_rows(text, n_threads)
+    assert len(got) == len(want) == 3
+    assert got == want
+
+
+def test_native_tokenizer_leaves_anything_unusual_to_python():
+    good = b"chr1\t10\t20\t+\tGT\tAG\t1,5,9\t3,2,1\n"
+    lines = [
+        good,
+        b"chr2\t7\t9\t-\tGT\tAG\t4\t11\r\n",                  # CRLF is what strip() removes: native
+        b" chr1\t10\t20\t+\tGT\tAG\t1,5\t3,2\n",              # leading blank
+        b"chr1\t10\t20\t+\tGT\tAG\t1,5\t3,2\t\n",             # trailing tab
+        b"chr1\t10\t20\t+\tGT\tAG\t1,05\t3,2\n",              # leading zero: another count_samples string
+        b"chr1\t10\t20\t+\tGT\tAG\t1,5,7\t3,2\n",             # unequal lists
+        b"chr1\t10\t20\t+\tGT\tAG\t1,-5\t3,2\n",              # sign
+        b"chr1\t10\t20\t+\tGT\tAG\t1, 5\t3,2\n",              # blank inside
+        b"chr1\t10\t20\n",                                      # too few fields
+        b"chr1\t10\t20\t+\tGT\tAG\t1,5\t3,99999999999\n",     # does not fit int32
+        b"chrX\t1\t2\tx\ty\t12,13\t1,1",                        # last line without newline, five fields
+    ]
+    text = b"".join(lines)
+    got = _native_rows(text, 4)
+    assert [g[0] == "python" for g in got] == [False, False, True, True, True, True, True, True, True, True, False]
+    assert got[0] == ("chr1 10 20", [1, 5, 9], [3, 2, 1])
+    assert got[1] == ("chr2 7 9", [4], [11])
+    assert got[10] == ("chrX 1 2", [12, 13], [1, 1])
+    for g, line in zip(got, lines):
+        if g[0] == "python":
+            assert g[1] == line                                 # the caller gets the exact bytes of the row back
+
+
+def test_native_tokenizer_random_rows_and_thread_counts():
+    from morna_b200 import parse
+    rng = np.random.default_rng(5)
+    rows = []
+    for j in range(2000):
+        n = int(rng.integers(1, 60))
+        s = np.sort(rng.choice(100000, size=n, replace=False))
+        c = rng.integers(1, 5000, size=n)
+        rows.append("chr%d\t%d\t%d\t+\tGT\tAG\t%s\t%s\n" % (rng.integers(1, 23), rng.integers(1, 1e8), rng.integers(1, 1e8),
+                                                          ",".join(map(str, s)), ",".join(map(str, c))))
+    text = "".join(rows).encode()
+    want = _python_rows(text)
+    for n_threads in (1, 2, 7, 32):
+        assert _native_rows(text, n_threads) == want
+    blocks = list(parse.read_blocks(io.BytesIO(text), block_bytes=4096))
+    assert b"".join(blocks) == text and all(b.endswith(b"\n") for b in blocks)
