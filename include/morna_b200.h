@@ -207,7 +207,9 @@ int morna_prepare_tensor_operand(const float *vectors, const double *pp, int64_t
 /* exact_search_nn for a batch of queries (morna.py:681-712) with the N x D contraction on the
  * tcgen05 tensor cores: fp16 scores with a rigorous error bound select a candidate superset
  * of the true top-k, which is re-ranked with the same FP64 sums as morna_knn_exact, so ids
- * and distances are identical to morna_knn_exact.  n <= 131072 rows per call.
+ * and distances are identical to morna_knn_exact.  n <= 2^24 rows per call; rows are scored in blocks of
+ * 131072 and between blocks every query's threshold is tightened to the k-th best score so far, so the
+ * candidate lists stay short however many rows the call covers.
  *   overflow [dev] uint8[nq]  1 where a candidate list overflowed (massive ties): those
  *                             queries hold id -1 / +inf and must be answered by morna_knn_exact
  *   stats    [dev] int32[4]   {overflowed queries, sum of first-pass survivors,

@@ -459,6 +459,7 @@ struct KthParams {
     const float *eps;
     float *thr;
     float *cand_score; int32_t *cand_id; int32_t *cand_cnt;
+    float *cand2_score; int32_t *cand2_id;        // refine mode: the compacted list goes here
     int32_t *fin_id; int32_t *fin_cnt;
     uint8_t *overflow; int32_t *stats;
 };
@@ -482,16 +483,20 @@ constexpr int kKwWarps = 8, kKwSlots = 32;            // one warp per query; 32 
 constexpr int kKwSmem = kKwWarps * 2 * 32 * kKwSlots * (int)sizeof(uint32_t);   // 64 KB
 
 // One WARP per query (8 queries per CTA, no block barriers).
-//   kPilot : input = dumped pilot scores -> thr[q] and the pilot's survivors start the candidate list
-//   !kPilot: input = candidate list      -> final candidate list
+//   kMode 1 (pilot) : input = dumped pilot scores -> thr[q] and the pilot's survivors start the candidate list
+//   kMode 0 (final) : input = candidate list      -> final candidate list
+//   kMode 2 (refine): input = candidate list      -> thr[q] tightened to (k-th largest so far) - 2 eps and the
+//                     list compacted into the second buffer; run between row blocks so that the list stays
+//                     short however many rows one call scores
 // A pivot taken from a 512-entry sample cuts the stream to a few hundred survivors that stay in
 // lane-private shared-memory lists; the exact k-th largest a_k of the survivors (= of all entries) is
 // found with warp-wide counts, and everything >= a_k - 2 eps is written out.  If the pivot misses
 // (too few survivors, a lane list overflows, or a_k - 2 eps falls below the pivot) the warp falls
 // back to a streaming bisection over all entries, which is exact for any input.
-template <bool kPilot>
+template <int kMode>
 __global__ void __launch_bounds__(kKwWarps * 32)
 kth_warp_kernel(KthParams p, int nq) {
+    constexpr bool kPilot = kMode == 1, kRefine = kMode == 2;
     extern __shared__ __align__(16) uint32_t kw_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = blockIdx.x * kKwWarps + warp;
@@ -503,13 +508,18 @@ kth_warp_kernel(KthParams p, int nq) {
     else {
         count = p.cand_cnt[q];
         if (count > p.cap) {            // survivors were dropped: the exact scan must answer this query
-            if (lane == 0) { if (!p.overflow[q]) atomicAdd(p.stats + 0, 1); p.overflow[q] = 1; p.fin_cnt[q] = 0; }
+            if (lane == 0) {
+                if (!p.overflow[q]) atomicAdd(p.stats + 0, 1);
+                p.overflow[q] = 1;
+                if (kRefine) { p.cand_cnt[q] = 0; p.thr[q] = INFINITY; }      // collect nothing more for it
+                else p.fin_cnt[q] = 0;
+            }
             return;
         }
     }
     const float *src = kPilot ? p.pilot + (int64_t)q * p.pilot_ld : p.cand_score + (int64_t)q * p.cap;
     const int kk = min(p.k, count);
-    const int out_cap = kPilot ? p.cap : p.fcap;
+    const int out_cap = (kPilot || kRefine) ? p.cap : p.fcap;
     const float eps = p.eps[q];
 
     uint32_t best = 0;          // key of the kk-th largest entry
@@ -572,6 +582,9 @@ kth_warp_kernel(KthParams p, int nq) {
             if (kPilot) {
                 p.cand_score[(int64_t)q * p.cap + at] = score;
                 p.cand_id[(int64_t)q * p.cap + at] = p.id_base + p.n_begin + idx;
+            } else if (kRefine) {
+                p.cand2_score[(int64_t)q * p.cap + at] = score;
+                p.cand2_id[(int64_t)q * p.cap + at] = p.cand_id[(int64_t)q * p.cap + idx];
             } else {
                 p.fin_id[(int64_t)q * p.fcap + at] = p.cand_id[(int64_t)q * p.cap + idx];
             }
@@ -593,9 +606,10 @@ kth_warp_kernel(KthParams p, int nq) {
         }
     }
     if (lane == 0) {
-        if (kPilot) {
+        if (kPilot || kRefine) {
             p.thr[q] = cut;
             p.cand_cnt[q] = out;                     // the filter pass appends after these
+            if (kRefine) atomicAdd(p.stats + 1, count - out);        // survivors dropped here still count as first-pass survivors
         } else {
             int kept = out;
             if (kept > p.fcap) { if (!p.overflow[q]) atomicAdd(p.stats + 0, 1); p.overflow[q] = 1; kept = 0; }
@@ -835,11 +849,13 @@ static int sm_count_b() {
     return sms;
 }
 
-constexpr int kCandCap = 4096, kFinCap = 1024, kPilotMax = kKthMax, kBatchedMaxRows = 131072;
+constexpr int kCandCap = 4096, kFinCap = 1024, kPilotMax = kKthMax;
+constexpr int64_t kBatchedMaxRows = (int64_t)1 << 24;      // rows one call may score (ids are int32; TMA row coordinate)
 
 // tuning knobs for experiments (morna_debug_set_tuning): GEMM variant and pipeline depth
 static int g_gemm_pair = 1;       // 1: CTA pairs (cta_group::2), 0: single CTAs
 static int g_gemm_stages = 4;
+static int g_block_rows = 131072;  // rows scored between two refinements of the candidate lists (key 9)
 static int g_rerank_rows = 8;     // candidate rows per warp pass of the re-rank (2, 4 or 8)
 static int g_rerank_phase_mb = 0;  // row range kept L2-resident per re-rank phase; 0 = never split into phases
 
@@ -871,13 +887,14 @@ static int launch_knn_gemm(const CUtensorMap &tmap_q, const CUtensorMap &tmap_s,
 }
 
 struct BatchWs {
-    size_t hq, qq, eps, pilot, thr, cand_score, cand_id, cand_cnt, fin_id, fin_cnt, fin_dist, total;
+    size_t hq, qq, eps, pilot, thr, cand_score, cand_id, cand2_score, cand2_id, cand_cnt, fin_id, fin_cnt, fin_dist, total;
     int64_t nq_pad, n0, pilot_ld;
 };
 static BatchWs batch_ws_layout(int64_t n, int64_t nq, int64_t ld_h) {
     BatchWs w{};
     w.nq_pad = (nq + 2 * gemm::BM - 1) / (2 * gemm::BM) * (2 * gemm::BM);      // CTA pairs own 256 query rows
     w.n0 = n < kPilotMax ? n : kPilotMax;
+    if (w.n0 > g_block_rows) w.n0 = g_block_rows;
     w.pilot_ld = (w.n0 + 3) / 4 * 4;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t at = off; off += align_up(bytes, 256); return at; };
@@ -888,6 +905,10 @@ static BatchWs batch_ws_layout(int64_t n, int64_t nq, int64_t ld_h) {
     w.thr = take((size_t)nq * sizeof(float));
     w.cand_score = take((size_t)nq * kCandCap * sizeof(float));
     w.cand_id = take((size_t)nq * kCandCap * sizeof(int32_t));
+    if (n > g_block_rows) {                       // several row blocks: the lists are refined between them (ping-pong)
+        w.cand2_score = take((size_t)nq * kCandCap * sizeof(float));
+        w.cand2_id = take((size_t)nq * kCandCap * sizeof(int32_t));
+    }
     w.cand_cnt = take((size_t)nq * sizeof(int32_t));
     w.fin_id = take((size_t)nq * kFinCap * sizeof(int32_t));
     w.fin_cnt = take((size_t)nq * sizeof(int32_t));
@@ -984,22 +1005,40 @@ extern "C" int morna_knn_batched_score(const void *hs, int64_t ld_h, const float
     kp.pilot = pilot; kp.pilot_ld = w.pilot_ld; kp.eps = eps; kp.thr = thr; kp.cand_score = cand_score;
     kp.cand_id = cand_id; kp.cand_cnt = cand_cnt; kp.fin_id = fin_id; kp.fin_cnt = fin_cnt; kp.overflow = overflow;
     kp.stats = stats;
-    MORNA_CUDA_TRY(cudaFuncSetAttribute(kth_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKwSmem));
-    MORNA_CUDA_TRY(cudaFuncSetAttribute(kth_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKwSmem));
+    MORNA_CUDA_TRY(cudaFuncSetAttribute(kth_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKwSmem));
+    MORNA_CUDA_TRY(cudaFuncSetAttribute(kth_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKwSmem));
+    MORNA_CUDA_TRY(cudaFuncSetAttribute(kth_warp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKwSmem));
     const unsigned kth_grid = (unsigned)((nq + kKwWarps - 1) / kKwWarps);
 
     rc = launch_gemm(0, (int32_t)w.n0, 0);                       // pilot block: dump scores
     if (rc != MORNA_OK) return rc;
     mark();                                                      // 2: pilot GEMM
-    kth_warp_kernel<true><<<kth_grid, kKwWarps * 32, kKwSmem, s>>>(kp, (int)nq);
+    kth_warp_kernel<1><<<kth_grid, kKwWarps * 32, kKwSmem, s>>>(kp, (int)nq);
     MORNA_LAUNCH_CHECK();
     mark();                                                      // 3: thresholds
-    if (w.n0 < n) {
-        rc = launch_gemm((int32_t)w.n0, (int32_t)n, 1);          // the rest: keep scores above thr
+    // the rest in blocks of g_block_rows rows: keep scores above thr; between blocks thr is tightened to the
+    // k-th best seen so far and the lists are compacted, so a later block adds ~k entries per query, not ~N/n0 * k
+    for (int64_t b0 = w.n0; b0 < n;) {
+        int64_t b1 = b0 == w.n0 ? (int64_t)g_block_rows : b0 + g_block_rows;
+        if (b1 > n || b1 <= b0) b1 = n;
+        rc = launch_gemm((int32_t)b0, (int32_t)b1, 1);
         if (rc != MORNA_OK) return rc;
+        b0 = b1;
+        if (b0 < n) {
+            kp.cand2_score = (float *)(ws + w.cand2_score);
+            kp.cand2_id = (int32_t *)(ws + w.cand2_id);
+            kth_warp_kernel<2><<<kth_grid, kKwWarps * 32, kKwSmem, s>>>(kp, (int)nq);
+            MORNA_LAUNCH_CHECK();
+            // the compacted lists are now the current ones
+            float *ts = kp.cand_score; kp.cand_score = kp.cand2_score; kp.cand2_score = ts;
+            int32_t *ti = kp.cand_id; kp.cand_id = kp.cand2_id; kp.cand2_id = ti;
+            const size_t to = w.cand_score; w.cand_score = w.cand2_score; w.cand2_score = to;
+            const size_t tj = w.cand_id; w.cand_id = w.cand2_id; w.cand2_id = tj;
+            gp.cand_score = kp.cand_score; gp.cand_id = kp.cand_id;
+        }
     }
-    mark();                                                      // 4: filter GEMM
-    kth_warp_kernel<false><<<kth_grid, kKwWarps * 32, kKwSmem, s>>>(kp, (int)nq);
+    mark();                                                      // 4: filter GEMM(s)
+    kth_warp_kernel<0><<<kth_grid, kKwWarps * 32, kKwSmem, s>>>(kp, (int)nq);
     MORNA_LAUNCH_CHECK();
     mark();                                                      // 5: final candidate lists
     return MORNA_OK;
@@ -1113,6 +1152,7 @@ extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
     else if (key == 4) morna::set_acc_pipelined(value);
     else if (key == 1) g_gemm_stages = value;
     else if (key == 5) g_rerank_rows = value;
+    else if (key == 9) g_block_rows = value >= 256 ? value : 131072;
     else if (key == 7) morna::set_acc_split(value);
     else if (key == 8) morna::set_acc_variant(value);
     else if (key == 6) g_rerank_phase_mb = value;

@@ -184,7 +184,7 @@ class MornaSearch(object):
         return out_ids, out_d
 
     # ------------------------------------------------------------------ batched search (tensor cores)
-    BATCH_BLOCK_ROWS = 131072        # rows per morna_knn_batched call
+    BATCH_BLOCK_ROWS = 1 << 24       # rows per morna_knn_batched call (the call itself walks 131072-row blocks)
 
     def enable_tensor_path(self):
         """Builds the fp16 tensor-core operand of the resident rows (once)."""

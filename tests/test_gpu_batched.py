@@ -216,3 +216,31 @@ def test_streaming_batches_handle_tie_overflow_and_row_blocks():
     wi, wd = srch.exact_search_batch(B, 20, tensor_cores=False)
     for gi, gd in srch.search_batches([B, B.astype(np.float64)], 20):
         assert np.array_equal(gi, wi) and np.array_equal(gd, wd)
+
+
+@pytest.mark.parametrize("block_rows", [256, 1024, 4096])
+def test_many_row_blocks_in_one_call_refine_thresholds(block_rows):
+    """One morna_knn_batched call over several internal row blocks: thresholds tightened and candidate lists
+    compacted between blocks; results stay those of the exact scan, ties and zero rows included."""
+    from morna_b200 import _lib
+    lib = _lib.load()
+    try:
+        assert lib.morna_debug_set_tuning(9, block_rows) == 0
+        rng = np.random.default_rng(block_rows)
+        n, d, nq, k = 9000, 96, 300, 40
+        S = rng.standard_normal((n, d)).astype(np.float32)
+        S[100:104] = S[99]                      # exact ties across the list
+        S[8000] = S[99]                         # ... and across blocks
+        S[n // 2] = 0.0
+        srch = make_search(S)
+        rows = rng.permutation(n)[:nq]
+        Q = S[rows].astype(np.float64)
+        Q[1::3] += 0.05 * rng.standard_normal((len(Q[1::3]), d))
+        Q[0] = S[99]
+        q = torch.from_numpy(Q).cuda()
+        e_ids, e_d = srch.exact_search_device(q, k)
+        b_ids, b_d = srch.batched_search_device(q, k)
+        assert srch.last_stats[0] == 0
+        assert torch.equal(b_ids, e_ids) and torch.equal(b_d, e_d)
+    finally:
+        lib.morna_debug_set_tuning(9, 131072)
