@@ -856,6 +856,8 @@ constexpr int64_t kBatchedMaxRows = (int64_t)1 << 24;      // rows one call may 
 static int g_gemm_pair = 1;       // 1: CTA pairs (cta_group::2), 0: single CTAs
 static int g_gemm_stages = 4;
 static int g_block_rows = 131072;  // rows scored between two refinements of the candidate lists (key 9)
+static int g_pilot_rows = kKthMax; // rows of the pilot block whose scores are dumped for the first thresholds (key 10)
+static int g_first_block = 0;      // rows up to the first refinement (key 11); 0 = g_block_rows
 static int g_rerank_rows = 8;     // candidate rows per warp pass of the re-rank (2, 4 or 8)
 static int g_rerank_phase_mb = 0;  // row range kept L2-resident per re-rank phase; 0 = never split into phases
 
@@ -893,7 +895,7 @@ struct BatchWs {
 static BatchWs batch_ws_layout(int64_t n, int64_t nq, int64_t ld_h) {
     BatchWs w{};
     w.nq_pad = (nq + 2 * gemm::BM - 1) / (2 * gemm::BM) * (2 * gemm::BM);      // CTA pairs own 256 query rows
-    w.n0 = n < kPilotMax ? n : kPilotMax;
+    w.n0 = n < g_pilot_rows ? n : g_pilot_rows;
     if (w.n0 > g_block_rows) w.n0 = g_block_rows;
     w.pilot_ld = (w.n0 + 3) / 4 * 4;
     size_t off = 0;
@@ -905,7 +907,7 @@ static BatchWs batch_ws_layout(int64_t n, int64_t nq, int64_t ld_h) {
     w.thr = take((size_t)nq * sizeof(float));
     w.cand_score = take((size_t)nq * kCandCap * sizeof(float));
     w.cand_id = take((size_t)nq * kCandCap * sizeof(int32_t));
-    if (n > g_block_rows) {                       // several row blocks: the lists are refined between them (ping-pong)
+    if (n > g_block_rows || (g_first_block > 0 && n > g_first_block)) {   // several row blocks: lists refined between them (ping-pong)
         w.cand2_score = take((size_t)nq * kCandCap * sizeof(float));
         w.cand2_id = take((size_t)nq * kCandCap * sizeof(int32_t));
     }
@@ -1019,7 +1021,7 @@ extern "C" int morna_knn_batched_score(const void *hs, int64_t ld_h, const float
     // the rest in blocks of g_block_rows rows: keep scores above thr; between blocks thr is tightened to the
     // k-th best seen so far and the lists are compacted, so a later block adds ~k entries per query, not ~N/n0 * k
     for (int64_t b0 = w.n0; b0 < n;) {
-        int64_t b1 = b0 == w.n0 ? (int64_t)g_block_rows : b0 + g_block_rows;
+        int64_t b1 = b0 == w.n0 ? (int64_t)(g_first_block > 0 ? g_first_block : g_block_rows) : b0 + g_block_rows;
         if (b1 > n || b1 <= b0) b1 = n;
         rc = launch_gemm((int32_t)b0, (int32_t)b1, 1);
         if (rc != MORNA_OK) return rc;
@@ -1153,6 +1155,8 @@ extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
     else if (key == 1) g_gemm_stages = value;
     else if (key == 5) g_rerank_rows = value;
     else if (key == 9) g_block_rows = value >= 256 ? value : 131072;
+    else if (key == 10) g_pilot_rows = value >= 256 && value <= kPilotMax ? value : kPilotMax;
+    else if (key == 11) g_first_block = value > 0 ? value : 0;
     else if (key == 7) morna::set_acc_split(value);
     else if (key == 8) morna::set_acc_variant(value);
     else if (key == 6) g_rerank_phase_mb = value;

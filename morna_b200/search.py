@@ -399,15 +399,18 @@ class BatchPipeline(object):
         q = torch.from_numpy(np.ascontiguousarray(queries)) if isinstance(queries, np.ndarray) else queries
         if q.dtype != torch.float32:
             q = q.to(torch.float64)
-        direct = q.is_pinned() and q.is_contiguous()
+        resident = q.is_cuda                 # queries already in HBM: no host->device copy
+        direct = resident or (q.is_pinned() and q.is_contiguous())
         self._size(sl, q.shape[0], q.dtype, staging=not direct)
         if direct:
             src = q                          # already page-locked: copied straight from the caller's buffer,
         else:                                # which must stay untouched until collect()
             sl.host_q.copy_(q)               # pageable source -> the slot's pinned staging buffer
             src = sl.host_q
+        if resident:
+            sl.stream.wait_stream(torch.cuda.current_stream(s.device))             # the caller's writes to q are done
         with torch.cuda.stream(sl.stream):
-            sl.qd = src.to(s.device, non_blocking=True).to(torch.float64)          # float32 widens exactly
+            sl.qd = src.to(s.device, non_blocking=True).to(torch.float64).contiguous()   # float32 widens exactly
             n = s.row_hi - s.row_lo
             if n == 0 or sl.nq == 0 or k > 512:
                 sl.parts = None
