@@ -95,17 +95,19 @@ first_position_smem_kernel(const int64_t *__restrict__ row_off, const uint8_t *_
     for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n_rows; j += warps_total) {
         if (!pass[j]) continue;
         const int64_t b = row_off[j], e = row_off[j + 1];
-        for (int64_t p0 = b; p0 < e; p0 += 256) {          // eight independent loads in flight per lane
-            int32_t sv[8];
+        for (int64_t p0 = b; p0 < e; p0 += 512) {          // sixteen independent loads in flight per lane
+            int32_t sv[16];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < 16; ++u) {
                 const int64_t p = p0 + u * 32 + lane;
                 sv[u] = p < e ? __ldg(sample + p) : -1;
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < 16; ++u) {
                 const int64_t p = p0 + u * 32 + lane;
-                if ((uint32_t)sv[u] <= (uint32_t)max_sample_id) {
+                // a warp meets its rows in increasing position order, so after a sample's first sighting in
+                // this CTA a plain read almost always ends the matter; the atomic is the rare case
+                if ((uint32_t)sv[u] <= (uint32_t)max_sample_id && (uint32_t)p < s_first[sv[u]]) {
                     const uint32_t old = atomicMin(&s_first[sv[u]], (uint32_t)p);
                     if ((uint32_t)p < old) atomicMin(&first_pos[sv[u]], (unsigned long long)p);
                 }
