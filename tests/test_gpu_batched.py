@@ -244,3 +244,38 @@ def test_many_row_blocks_in_one_call_refine_thresholds(block_rows):
         assert torch.equal(b_ids, e_ids) and torch.equal(b_d, e_d)
     finally:
         lib.morna_debug_set_tuning(9, 131072)
+
+
+def test_headline_shape_properties():
+    """BASELINE configs[2] at full size (50,000 x 3000, 4096 in-index queries, k = 100): properties that do not
+    need the oracle -- every query finds itself first at distance exactly 0, lists are ordered under the reference
+    rule with distinct ids, no query overflows on Gaussian data -- plus bit equality with the exact scan and with the
+    single-query kernel on a sample of the queries."""
+    g = torch.Generator(device="cuda"); g.manual_seed(1234)
+    n, d, nq, k = 50000, 3000, 4096, 100
+    S = torch.randn((n, d), generator=g, device="cuda")
+    srch = make_search(S)
+    rows = torch.randperm(n, generator=torch.Generator().manual_seed(99))[:nq].cuda()
+    q = S[rows].double()
+    ids, dist = srch.batched_search_device(q, k)
+    assert srch.last_stats[0] == 0
+    assert torch.equal(ids[:, 0].long(), rows) and float(dist[:, 0].abs().max()) == 0.0
+    assert bool((dist[:, 1:] >= dist[:, :-1]).all())
+    tie = dist[:, 1:] == dist[:, :-1]
+    assert bool((ids[:, 1:][tie] < ids[:, :-1][tie]).all())              # equal distances: larger id first
+    srt = ids.sort(dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all()) and int(ids.min()) >= 0 and int(ids.max()) < n
+    pick = torch.arange(0, nq, 97, device="cuda")
+    e_ids, e_d = srch.exact_search_device(q[pick], k, allow_single=False)
+    assert torch.equal(ids[pick], e_ids) and torch.equal(dist[pick], e_d)
+    for j in pick[:5].tolist():
+        s_ids, s_d = srch.single_search_device(q[j], k)
+        assert torch.equal(s_ids[0], ids[j]) and torch.equal(s_d[0], dist[j])
+    # rows-sharded: the union of two shards' exact top-k merged equals the unsharded answer
+    from morna_b200 import dist as mdist
+    parts = []
+    for r in range(2):
+        sh = make_search(S, shard=(r, 2))
+        parts.append(sh.batched_search_device(q[pick], k))
+    m_ids, m_d = mdist.merge_topk(torch.cat([p[0] for p in parts], 1), torch.cat([p[1] for p in parts], 1), k)
+    assert torch.equal(m_ids, ids[pick]) and torch.equal(m_d, dist[pick])

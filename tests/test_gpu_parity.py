@@ -442,3 +442,38 @@ def test_index_from_text_blocks_equals_index_from_python_rows(tmp_path):
     c = go_index(path, str(tmp_path / "idx"), 200, None, None, 4, 1024, False, None, out=io.StringIO())
     assert c.sample_count == n_samples
     assert np.array_equal(c.matrix_f32(), a.matrix_f32())
+
+
+def test_index_build_properties_at_scale():
+    """A few million pairs through the C ABI (too many for the Python oracle): the warp-per-range and the
+    barrier-per-row scatter-add give the same doubles; doubling every coverage doubles every cell exactly (powers of
+    two commute with each rounding the reference performs); two runs are identical (no atomics on the path)."""
+    from morna_b200 import _lib
+    from morna_b200.index import MornaIndex
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    n_samples, n_rows, dim = 6000, 9000, 500
+    lens = np.clip(rng.lognormal(5.0, 1.2, size=n_rows).astype(np.int64), 1, n_samples)
+    def build(scale, variant):
+        lib.morna_debug_set_tuning(8, variant)
+        try:
+            idx = MornaIndex(n_samples, "unused", dim=dim, sample_threshold=50)
+            r = np.random.default_rng(5)
+            for j in range(n_rows):
+                samples = np.sort(r.choice(n_samples, size=int(lens[j]), replace=False)) + 1
+                covs = (1 + r.geometric(0.4, size=int(lens[j]))) * scale
+                idx._rows.add("chr%d %d %d" % (j % 22 + 1, 1000 + 7 * j, 1500 + 7 * j), samples, covs)
+                passing = int(lens[j] >= 50)
+                idx._pass.append(passing); idx._running_freq.append(int(lens[j]) if passing else 0)
+            idx.build()
+            return idx.accumulator_f64(), idx.matrix_f32(), idx.internal_id_map
+        finally:
+            lib.morna_debug_set_tuning(8, 3)
+    a1, m1, map1 = build(1, 4)          # 4: the warp-per-range variant whatever the rows-per-bucket heuristic says
+    a1b, m1b, _ = build(1, 4)
+    a0, m0, map0 = build(1, 0)          # 0: barrier-per-row variants only
+    a2, m2, _ = build(2, 4)
+    assert int((lens >= 50).sum()) > 5000 and float(np.abs(a1).max()) > 0
+    assert map1 == map0 and np.array_equal(a1, a0) and np.array_equal(m1, m0)      # both scatter-add variants
+    assert np.array_equal(a1, a1b) and np.array_equal(m1, m1b)                     # deterministic
+    assert np.array_equal(a2, 2.0 * a1) and np.array_equal(m2, 2.0 * m1)           # exact linearity in the coverages
