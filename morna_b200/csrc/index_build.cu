@@ -404,12 +404,16 @@ row_segments_kernel(const int64_t *__restrict__ row_off, const int8_t *__restric
 }
 
 struct WarpMeta { double w[32]; int32_t pos[32]; int32_t n[32]; };      // one batch of 32 rows, this warp's range
+struct WarpSlots { double w[2][kAcc3Group]; };                           // +-idf of the chunks in flight
 
 // One warp = (bucket, sample-id range): the bucket's rows in file order, for each row the pairs whose
-// sample id falls in the range.  Software pipeline: the rows' metadata is fetched one batch of 32 rows
-// ahead, the first 32 pairs of the next group of eight rows are in flight while the current group is
-// applied.  Runs only if rows_ascending_kernel found every passing row strictly ascending (otherwise
-// the binary-searched segments mean nothing and the barrier-per-row variants do the work).
+// sample id falls in the range.  The work is cut into chunks of up to 32 consecutive pairs of one
+// row (a row's segment of n pairs is ceil(n/32) chunks; an empty segment is none); a uniform software
+// pipeline keeps the loads of the next eight chunks in flight while the current eight are added, and
+// the rows' metadata is fetched one batch of 32 rows ahead.  A __syncwarp() follows the last chunk of
+// each row, so rows are applied in file order; the chunks of one row hold distinct samples.  Runs only
+// if rows_monotonic_kernel found every passing row strictly ascending (otherwise the binary-searched
+// segments mean nothing and the barrier-per-row variants do the work).
 __global__ void __launch_bounds__(kAcc3Threads)
 index_accumulate3_kernel(const int32_t *__restrict__ not_ascending, const int32_t *__restrict__ sample,
                          const int32_t *__restrict__ cov, const int32_t *__restrict__ id_of_sample,
@@ -424,13 +428,16 @@ index_accumulate3_kernel(const int32_t *__restrict__ not_ascending, const int32_
     if (range >= n_ranges) return;                             // no block-wide barrier below
     const int32_t width = 1 << shift, range_lo = range << shift;
     double *slice = reinterpret_cast<double *>(smem_raw) + (size_t)warp * width;
-    WarpMeta *wm = reinterpret_cast<WarpMeta *>(reinterpret_cast<double *>(smem_raw) + (size_t)kAcc3Warps * width) + 2 * warp;
+    unsigned char *after = smem_raw + (size_t)kAcc3Warps * width * sizeof(double);
+    WarpMeta *wm = reinterpret_cast<WarpMeta *>(after) + 2 * warp;
+    WarpSlots *ws = reinterpret_cast<WarpSlots *>(after + (size_t)kAcc3Warps * 2 * sizeof(WarpMeta)) + warp;
     const int32_t r_begin = bucket_begin[b], r_end = bucket_begin[b + 1];
     const int nrows = r_end - r_begin;
     if (nrows == 0) return;                                    // acc was zero-filled by the caller
     for (int i = lane; i < width; i += 32) slice[i] = 0.0;
-    const int n_groups = (nrows + kAcc3Group - 1) / kAcc3Group, n_batches = (nrows + 31) / 32;
-    // stage A: this lane's row of a batch -> registers; published to shared memory one batch ahead of use
+    const int n_batches = (nrows + 31) / 32;
+
+    // this lane's row of a metadata batch -> registers; published to shared memory when the cursor reaches the batch
     int32_t a_pos = 0, a_n = 0;
     double a_w = 0.0;
     auto fetch_meta = [&](int batch) {
@@ -444,71 +451,63 @@ index_accumulate3_kernel(const int32_t *__restrict__ not_ascending, const int32_
         }
     };
     auto publish_meta = [&](int batch) {
+        __syncwarp();                                          // nobody still reads the buffer being replaced
         WarpMeta &m = wm[batch & 1];
         m.pos[lane] = a_pos; m.n[lane] = a_n; m.w[lane] = a_w;
         __syncwarp();
     };
-    // stage B: first 32 pairs of each row of a group, all loads in flight together
-    auto issue = [&](int g, int32_t (&ps)[kAcc3Group], int32_t (&pc)[kAcc3Group]) {
-        if ((g & 3) == 0) {                                    // first group of a batch: its rows' metadata becomes visible,
-            publish_meta(g >> 2);                              // and the next batch's starts to load
-            fetch_meta((g >> 2) + 1);
-        }
-        const WarpMeta &m = wm[(g >> 2) & 1];
+    // cursor over the chunk stream: row cur_r (relative to r_begin), offset cur_c into its segment
+    int cur_r = -1, cur_c = 0, cur_n = 0, cur_pos = 0;
+    double cur_w = 0.0;
+    // fills one group: descriptors (pairs in the chunk | last-of-row flag << 8; 0 = no chunk) and the loads
+    auto issue = [&](int buf, int32_t (&desc)[kAcc3Group], int32_t (&ps)[kAcc3Group], int32_t (&pc)[kAcc3Group]) {
+        bool any = false;
 #pragma unroll
         for (int u = 0; u < kAcc3Group; ++u) {
-            const int t = (g & 3) * kAcc3Group + u;
-            const bool have = lane < m.n[t];
-            const int32_t pos = m.pos[t];
-            ps[u] = have ? __ldg(sample + pos + lane) : -1;
-            pc[u] = have ? __ldg(cov + pos + lane) : 0;
+            while (cur_r < nrows && cur_c >= cur_n) {          // next row with pairs left in this range
+                ++cur_r; cur_c = 0;
+                if (cur_r < nrows) {
+                    if ((cur_r & 31) == 0) { publish_meta(cur_r >> 5); fetch_meta((cur_r >> 5) + 1); }
+                    const WarpMeta &m = wm[(cur_r >> 5) & 1];
+                    cur_n = m.n[cur_r & 31]; cur_pos = m.pos[cur_r & 31]; cur_w = m.w[cur_r & 31];
+                } else cur_n = 0;
+            }
+            desc[u] = 0; ps[u] = -1; pc[u] = 0;
+            if (cur_r < nrows) {
+                const int32_t cnt = min(32, cur_n - cur_c);
+                if (lane < cnt) { ps[u] = __ldg(sample + cur_pos + cur_c + lane); pc[u] = __ldg(cov + cur_pos + cur_c + lane); }
+                cur_c += cnt;
+                desc[u] = cnt | ((cur_c >= cur_n) << 8);
+                if (lane == 0) ws->w[buf][u] = cur_w;
+                any = true;
+            }
         }
+        __syncwarp();
+        return any;
     };
-    // stage C: the group's rows applied in file order
-    auto apply = [&](int g, const int32_t (&ps)[kAcc3Group], const int32_t (&pc)[kAcc3Group]) {
-        const WarpMeta &m = wm[(g >> 2) & 1];
+    auto apply = [&](int buf, const int32_t (&desc)[kAcc3Group], const int32_t (&ps)[kAcc3Group], const int32_t (&pc)[kAcc3Group]) {
 #pragma unroll
         for (int u = 0; u < kAcc3Group; ++u) {
-            const int t = (g & 3) * kAcc3Group + u;
-            if (g * kAcc3Group + u >= nrows) break;
-            const double w = m.w[t];
-            const int32_t n = m.n[t];
+            if (desc[u] == 0) break;
             if (ps[u] >= 0) {
                 double *cell = slice + (ps[u] - range_lo);
-                *cell = __dadd_rn(*cell, __dmul_rn((double)pc[u], w));          // product rounded, then added: as the reference
+                *cell = __dadd_rn(*cell, __dmul_rn((double)pc[u], ws->w[buf][u]));   // product rounded, then added: as the reference
             }
-            if (n > 32) {                                      // long segment: the rest of the row, four chunks at a time
-                const int32_t pos = m.pos[t];
-                for (int32_t c = 32; c < n; c += 32 * kAcc3Unroll) {
-                    int32_t qs[kAcc3Unroll], qc[kAcc3Unroll];
-#pragma unroll
-                    for (int v = 0; v < kAcc3Unroll; ++v) {
-                        const int32_t i = c + 32 * v + lane;
-                        qs[v] = i < n ? __ldg(sample + pos + i) : -1;
-                        qc[v] = i < n ? __ldg(cov + pos + i) : 0;
-                    }
-#pragma unroll
-                    for (int v = 0; v < kAcc3Unroll; ++v)
-                        if (qs[v] >= 0) {
-                            double *cell = slice + (qs[v] - range_lo);
-                            *cell = __dadd_rn(*cell, __dmul_rn((double)qc[v], w));
-                        }
-                }
-            }
-            __syncwarp();                                      // rows are applied in file order
+            if (desc[u] >> 8) __syncwarp();                    // the row is complete: rows are applied in file order
         }
     };
 
     fetch_meta(0);
-    int32_t sa[kAcc3Group], ca[kAcc3Group], sb[kAcc3Group], cb[kAcc3Group];
-    issue(0, sa, ca);                                          // (publishes batch 0, starts batch 1's metadata)
-    for (int g = 0; g < n_groups; g += 2) {
-        if (g + 1 < n_groups) issue(g + 1, sb, cb);            // next group's loads fly during this group's adds
-        apply(g, sa, ca);
-        if (g + 1 >= n_groups) break;
-        if (g + 2 < n_groups) issue(g + 2, sa, ca);
-        apply(g + 1, sb, cb);
+    int32_t da[kAcc3Group], sa[kAcc3Group], ca[kAcc3Group], db[kAcc3Group], sb[kAcc3Group], cb[kAcc3Group];
+    bool more = issue(0, da, sa, ca);
+    while (more) {
+        const bool more_b = issue(1, db, sb, cb);              // next group's loads fly during this group's adds
+        apply(0, da, sa, ca);
+        if (!more_b) break;
+        more = issue(0, da, sa, ca);
+        apply(1, db, sb, cb);
     }
+    __syncwarp();
     // the slice is in sample-id order; the accumulator is indexed by internal id
     double *out = acc + (int64_t)b * acc_ld;
     for (int i = lane; i < width; i += 32) {
@@ -587,10 +586,12 @@ static AccWs acc_ws_layout(int64_t n_rows, int32_t dim) {
 
 static int g_acc_pipelined = 1;      // morna_debug_set_tuning key 4
 static int g_acc_split = 1;          // morna_debug_set_tuning key 7: id tiles per bucket column (more CTAs per SM)
+static int g_acc_shift = 10;         // morna_debug_set_tuning key 12: log2 of the sample-id range width (>= 10)
 static int g_acc_variant = 3;        // morna_debug_set_tuning key 8: 3 = sample-range warps first, else barrier-per-row only
 void set_acc_pipelined(int v) { g_acc_pipelined = v ? 1 : 0; }
 void set_acc_split(int v) { g_acc_split = v > 0 ? v : 1; }
 void set_acc_variant(int v) { g_acc_variant = v; }
+void set_acc_shift(int v) { g_acc_shift = v >= 10 && v <= 12 ? v : 10; }
 
 static unsigned grid_for(int64_t work, int threads) {
     int64_t g = (work + threads - 1) / threads;
@@ -725,7 +726,7 @@ extern "C" int morna_index_accumulate(const int64_t *row_off, const uint8_t *pas
     const bool enough_rows = g_acc_variant == 4 || n_rows / dim >= 64 || n_rows < 4096;
     if ((g_acc_variant == 3 || g_acc_variant == 4) && enough_rows && nnz < 0x7fffffff) {
         // sample-id ranges of 2^shift ids, at most kAcc3MaxRanges of them, at least 1024 ids wide
-        int32_t shift = 10;
+        int32_t shift = g_acc_shift;
         while (((int64_t)max_sample_id >> shift) + 1 > kAcc3MaxRanges) ++shift;
         const int32_t n_ranges = (int32_t)(((int64_t)max_sample_id >> shift) + 1);
         auto *seg = (int32_t *)(ws + w.seg);
@@ -733,7 +734,7 @@ extern "C" int morna_index_accumulate(const int64_t *row_off, const uint8_t *pas
         row_segments_kernel<<<grid_for(n_rows * (n_ranges + 1), 256), 256, 0, s>>>(row_off, sign, idf, sample, vals_out, begin,
                                                                                  dim, shift, n_ranges, seg, meta);
         MORNA_LAUNCH_CHECK();
-        const size_t smem3 = (size_t)kAcc3Warps * (((size_t)1 << shift) * sizeof(double) + 2 * sizeof(WarpMeta));
+        const size_t smem3 = (size_t)kAcc3Warps * (((size_t)1 << shift) * sizeof(double) + 2 * sizeof(WarpMeta) + sizeof(WarpSlots));
         if (smem3 <= 200 * 1024) {
             MORNA_CUDA_TRY(cudaFuncSetAttribute(index_accumulate3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
             dim3 grid3((unsigned)dim, (unsigned)((n_ranges + kAcc3Warps - 1) / kAcc3Warps));

@@ -1146,7 +1146,7 @@ extern "C" int morna_debug_tensor_scores(const void *hs, int64_t ld_h, const flo
 
 /* Experiment knobs, process-wide: key 0 = GEMM variant (1 CTA pairs / 0 single CTA),
  * key 1 = shared-memory pipeline stages of the pair variant (4 or 6). */
-namespace morna { void set_single_tma(int v); void set_acc_pipelined(int v); void set_acc_split(int v); void set_acc_variant(int v); }
+namespace morna { void set_single_tma(int v); void set_acc_pipelined(int v); void set_acc_split(int v); void set_acc_variant(int v); void set_acc_shift(int v); }
 
 extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
     if (key == 0) g_gemm_pair = value ? 1 : 0;
@@ -1159,6 +1159,7 @@ extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
     else if (key == 11) g_first_block = value > 0 ? value : 0;
     else if (key == 7) morna::set_acc_split(value);
     else if (key == 8) morna::set_acc_variant(value);
+    else if (key == 12) morna::set_acc_shift(value);
     else if (key == 6) g_rerank_phase_mb = value;
 
     else return MORNA_ERR_INVALID_ARGUMENT;

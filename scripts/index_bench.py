@@ -14,7 +14,7 @@ ap.add_argument("--samples", type=int, default=21504)
 ap.add_argument("--dims", type=str, default="500,1000,3000,10000,30000")
 ap.add_argument("--threshold", type=int, default=100)
 ap.add_argument("--cpu-pairs", type=float, default=5e6)
-ap.add_argument("--splits", type=str, default="", help="sweep morna_debug_set_tuning key 7 (id tiles per bucket column)")
+ap.add_argument("--splits", type=str, default="", help="sweep morna_debug_set_tuning key 12 (log2 width of the sample-id ranges of the warp-per-range scatter-add)")
 args = ap.parse_args()
 lib = _lib.load()
 dev = torch.device("cuda")
@@ -87,12 +87,12 @@ for dim in [int(x) for x in args.dims.split(",")]:
     d_acc = torch.empty(dim * acc_ld, dtype=torch.float64, device=dev)
     ws_acc = _lib.workspace(lib.morna_index_accumulate_workspace_bytes(J, dim), dev)
     for split in [int(x) for x in args.splits.split(",") if x]:
-        lib.morna_debug_set_tuning(7, split)
+        lib.morna_debug_set_tuning(12, split)
         t_s = timed(lambda: _lib.check(lib.morna_index_accumulate(_lib.dev_ptr(d_row_off), _lib.dev_ptr(d_pass), _lib.dev_ptr(d_bucket), _lib.dev_ptr(d_sign),
                     _lib.dev_ptr(d_idf), J, _lib.dev_ptr(d_sample), _lib.dev_ptr(d_cov), nnz, _lib.dev_ptr(d_id_of), N, 0, n_kept, dim, _lib.dev_ptr(d_acc),
                     acc_ld, _lib.dev_ptr(ws_acc), ws_acc.numel(), sp), "acc"), reps=2)
-        print("D=%5d: id tiles per column %d -> accumulate %.2f ms" % (dim, split, t_s), flush=True)
-        lib.morna_debug_set_tuning(7, 1)
+        print("D=%5d: sample-id range width 2^%d -> accumulate %.2f ms" % (dim, split, t_s), flush=True)
+        lib.morna_debug_set_tuning(12, 10)
     t_acc = timed(lambda: _lib.check(lib.morna_index_accumulate(_lib.dev_ptr(d_row_off), _lib.dev_ptr(d_pass), _lib.dev_ptr(d_bucket), _lib.dev_ptr(d_sign),
                   _lib.dev_ptr(d_idf), J, _lib.dev_ptr(d_sample), _lib.dev_ptr(d_cov), nnz, _lib.dev_ptr(d_id_of), N, 0, n_kept, dim, _lib.dev_ptr(d_acc),
                   acc_ld, _lib.dev_ptr(ws_acc), ws_acc.numel(), sp), "acc"), reps=2)
