@@ -184,8 +184,8 @@ def main():
     def step_resident():
         ids, d = srch.batched_search_device(queries64, K)
         if args.rows_sharded and world > 1:
-            ids, d = mdist.all_gather_topk(ids, d)
-            ids, d = mdist.merge_topk(ids, d, K)
+            gi, gd = mdist.all_gather_sorted(ids, d)
+            ids, d = mdist.merge_sorted_lists(gi, gd, K)
         return ids, d
 
     def step_e2e():
@@ -193,8 +193,8 @@ def main():
         q = host_q.to(device, non_blocking=True).to(torch.float64)   # widened exactly on the device
         ids, d = srch.batched_search_device(q, K)
         if args.rows_sharded and world > 1:
-            ids, d = mdist.all_gather_topk(ids, d)
-            ids, d = mdist.merge_topk(ids, d, K)
+            gi, gd = mdist.all_gather_sorted(ids, d)
+            ids, d = mdist.merge_sorted_lists(gi, gd, K)
         host_ids.copy_(ids, non_blocking=True)
         host_d.copy_(d, non_blocking=True)
         torch.cuda.current_stream().synchronize()

@@ -166,6 +166,13 @@ int morna_select_topk(const double *keys, const int32_t *ids, int64_t n, int64_t
                       int32_t *out_ids, double *out_dist,
                       void *workspace, size_t workspace_bytes, void *stream);
 
+/* Merge of per-shard exact top-k lists (the one exchange step of the row-sharded search): n_lists lists
+ * per query, each sorted under the reference order and padded with id -1 / +inf, laid out
+ * [n_lists][nq][k_in] as an all-gather of [nq][k_in] tensors leaves them.  Equal to morna_select_topk
+ * over the concatenation (ids are distinct across shards), by rank counting instead of a selection. */
+int morna_merge_sorted_topk(const double *dists, const int32_t *ids, int32_t n_lists, int64_t nq,
+                            int32_t k_in, int32_t k_out, int32_t *out_ids, double *out_dist, void *stream);
+
 /* exact_search_nn for nq queries in one call (morna.py:681-712): distances + top-k.
  * Internally tiles the queries so the distance scratch stays bounded. */
 size_t morna_knn_exact_workspace_bytes(int64_t n, int64_t nq, int32_t k);

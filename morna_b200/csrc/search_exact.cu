@@ -328,6 +328,72 @@ extern "C" size_t morna_select_topk_workspace_bytes(int64_t n, int64_t nq, int32
     return 2 * (align_up(entries * sizeof(double), 256) + align_up(entries * sizeof(int32_t), 256)) + 256;
 }
 
+namespace morna {
+
+// K7 merge of per-shard results: G lists per query, each already sorted under the reference rule
+// (distance ascending, equal distances id descending; padding = id -1 / +inf at the tail).  One CTA
+// per query; every entry finds its global rank as its position in its own list plus, for every other
+// list, the number of entries that come before it (binary search), and entries of rank < k_out are
+// written straight to their place.  Input layout [G][nq][k_in], as an all-gather of [nq][k_in]
+// tensors leaves it.
+constexpr int kMergeThreads = 128;
+
+__global__ void __launch_bounds__(kMergeThreads)
+merge_sorted_topk_kernel(const double *__restrict__ dists, const int32_t *__restrict__ ids, int32_t n_lists, int64_t nq,
+                         int32_t k_in, int32_t k_out, int32_t *__restrict__ out_ids, double *__restrict__ out_dist) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sd = reinterpret_cast<double *>(smem_raw);                 // [n_lists * k_in]
+    int32_t *si = reinterpret_cast<int32_t *>(sd + (size_t)n_lists * k_in);
+    const int64_t q = blockIdx.x;
+    const int total = n_lists * k_in;
+    for (int e = threadIdx.x; e < total; e += kMergeThreads) {
+        const int g = e / k_in, j = e - g * k_in;
+        const int64_t src = ((int64_t)g * nq + q) * k_in + j;
+        sd[e] = dists[src]; si[e] = ids[src];
+    }
+    for (int i = threadIdx.x; i < k_out; i += kMergeThreads) { out_ids[q * k_out + i] = -1; out_dist[q * k_out + i] = INFINITY; }
+    __syncthreads();
+    for (int e = threadIdx.x; e < total; e += kMergeThreads) {
+        const int id = si[e];
+        if (id < 0) continue;                                          // padding never outranks a real entry
+        const double d = sd[e];
+        const int g = e / k_in;
+        int rank = e - g * k_in;                                       // entries before it in its own list
+        for (int h = 0; h < n_lists; ++h) {
+            if (h == g) continue;
+            const double *ld = sd + h * k_in;
+            const int32_t *li = si + h * k_in;
+            int lo = 0, hi = k_in;                                     // first entry of list h that does NOT come before (d, id)
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (li[mid] >= 0 && before(ld[mid], li[mid], d, id)) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < k_out) { out_ids[q * k_out + rank] = id; out_dist[q * k_out + rank] = d; }
+    }
+}
+
+}  // namespace morna
+
+extern "C" int morna_merge_sorted_topk(const double *dists, const int32_t *ids, int32_t n_lists, int64_t nq, int32_t k_in,
+                                       int32_t k_out, int32_t *out_ids, double *out_dist, void *stream) {
+    if (!dists || !ids || !out_ids || !out_dist || n_lists <= 0 || nq < 0 || k_in <= 0 || k_out <= 0)
+        return MORNA_ERR_INVALID_ARGUMENT;
+    if (nq == 0) return MORNA_OK;
+    const size_t smem = (size_t)n_lists * k_in * (sizeof(double) + sizeof(int32_t));
+    if (smem > 200 * 1024 || nq > 0x7fffffff) return MORNA_ERR_INVALID_ARGUMENT;
+    static size_t attr = 0;
+    if (smem > attr) {
+        MORNA_CUDA_TRY(cudaFuncSetAttribute(morna::merge_sorted_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    morna::merge_sorted_topk_kernel<<<(unsigned)nq, morna::kMergeThreads, smem, (cudaStream_t)stream>>>(
+        dists, ids, n_lists, nq, k_in, k_out, out_ids, out_dist);
+    MORNA_LAUNCH_CHECK();
+    return MORNA_OK;
+}
+
 extern "C" int morna_select_topk(const double *keys, const int32_t *ids, int64_t n, int64_t key_ld,
                                  int32_t id_base, int64_t nq, int32_t k, int32_t *out_ids,
                                  double *out_dist, void *workspace, size_t workspace_bytes, void *stream) {

@@ -43,6 +43,34 @@ def merge_topk(ids, dists, k, stream=None):
     return out_i, out_d
 
 
+def merge_sorted_lists(ids, dists, k, stream=None):
+    """Exact top-k of G sorted lists per query.  ids int32 / dists float64 [G x nq x k_in] on the GPU, every
+    list sorted under the reference order (what each shard's search returns), padding id -1 / +inf."""
+    lib = _lib.load()
+    assert ids.is_cuda and dists.is_cuda and ids.shape == dists.shape and ids.dim() == 3
+    ids = ids.contiguous().to(torch.int32)
+    dists = dists.contiguous().to(torch.float64)
+    g, nq, k_in = ids.shape
+    out_i = torch.empty((nq, k), dtype=torch.int32, device=ids.device)
+    out_d = torch.empty((nq, k), dtype=torch.float64, device=ids.device)
+    with torch.cuda.device(ids.device):
+        _lib.check(lib.morna_merge_sorted_topk(_lib.dev_ptr(dists), _lib.dev_ptr(ids), g, nq, k_in, k,
+                                               _lib.dev_ptr(out_i), _lib.dev_ptr(out_d), _lib.stream_ptr(stream)),
+                   "morna_merge_sorted_topk")
+    return out_i, out_d
+
+
+def all_gather_sorted(ids, dists, group=None):
+    """Every rank's [nq x k] lists -> [world x nq x k] (one collective per tensor, no concatenation)."""
+    import torch.distributed as td
+    world = td.get_world_size(group)
+    gi = torch.empty((world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
+    gd = torch.empty((world,) + tuple(dists.shape), dtype=dists.dtype, device=dists.device)
+    td.all_gather_into_tensor(gi, ids.contiguous(), group=group)
+    td.all_gather_into_tensor(gd, dists.contiguous(), group=group)
+    return gi, gd
+
+
 def all_gather_topk(ids, dists, group=None):
     """Gather every rank's [nq x k] lists -> [nq x world*k], rank-major along dim 1."""
     import torch.distributed as td
@@ -56,12 +84,17 @@ def all_gather_topk(ids, dists, group=None):
     return torch.cat(gi, dim=1), torch.cat(gd, dim=1)
 
 
-def sharded_exact_search(local_search, queries, k, group=None, merge=merge_topk):
-    """`local_search(queries, k)` -> this rank's (ids, dists) with GLOBAL internal ids.
-    Returns the merged global (ids, dists), identical on every rank."""
-    ids, dists = local_search(queries, k)
-    ids, dists = all_gather_topk(ids, dists, group)
+def sharded_exact_search(local_search, queries, k, group=None, merge=None):
+    """`local_search(queries, k)` -> this rank's (ids, dists) with GLOBAL internal ids, sorted under the
+    reference order.  Returns the merged global (ids, dists), identical on every rank.  On the GPU the
+    lists are gathered as [world x nq x k] and merged by rank counting (morna_merge_sorted_topk); a
+    `merge(ids [nq x world*k], dists, k)` callable replaces that (CPU tests pass the oracle's rule)."""
     import torch.distributed as td
-    if td.is_available() and td.is_initialized() and td.get_world_size(group) > 1:
-        return merge(ids, dists, k)
-    return ids, dists
+    ids, dists = local_search(queries, k)
+    if not (td.is_available() and td.is_initialized() and td.get_world_size(group) > 1):
+        return ids, dists
+    if merge is None and ids.is_cuda:
+        gi, gd = all_gather_sorted(ids, dists, group)
+        return merge_sorted_lists(gi, gd, k)
+    ids, dists = all_gather_topk(ids, dists, group)
+    return (merge or merge_topk)(ids, dists, k)

@@ -477,3 +477,28 @@ def test_index_build_properties_at_scale():
     assert map1 == map0 and np.array_equal(a1, a0) and np.array_equal(m1, m0)      # both scatter-add variants
     assert np.array_equal(a1, a1b) and np.array_equal(m1, m1b)                     # deterministic
     assert np.array_equal(a2, 2.0 * a1) and np.array_equal(m2, 2.0 * m1)           # exact linearity in the coverages
+
+
+@pytest.mark.parametrize("n_lists,nq,k_in,k_out", [(8, 300, 100, 100), (2, 5, 7, 7), (3, 64, 20, 10), (4, 33, 16, 40)])
+def test_merge_of_sorted_lists_equals_generic_selection(n_lists, nq, k_in, k_out):
+    """morna_merge_sorted_topk (rank counting over per-shard sorted lists) == morna_select_topk over the
+    concatenation, with ties across lists, short lists (padding) and k_out above and below k_in."""
+    from morna_b200 import dist as mdist
+    rng = np.random.default_rng(n_lists * 1000 + nq)
+    total = n_lists * k_in
+    ids = np.full((n_lists, nq, k_in), -1, np.int32)
+    d = np.full((n_lists, nq, k_in), np.inf)
+    for q in range(nq):
+        perm = rng.permutation(10 * total)[:total].astype(np.int32)           # distinct ids across the lists
+        vals = np.round(rng.random(total), 2)                                 # two decimals: many equal distances
+        for g in range(n_lists):
+            m = k_in if (q + g) % 5 else int(rng.integers(0, k_in))           # some lists are short
+            li, lv = perm[g * k_in:g * k_in + m], vals[g * k_in:g * k_in + m]
+            order = np.lexsort((-li, lv))                                     # distance ascending, id descending
+            ids[g, q, :m], d[g, q, :m] = li[order], lv[order]
+    ti, td_ = torch.from_numpy(ids).cuda(), torch.from_numpy(d).cuda()
+    got_i, got_d = mdist.merge_sorted_lists(ti, td_, k_out)
+    flat_i = ti.permute(1, 0, 2).reshape(nq, total)
+    flat_d = td_.permute(1, 0, 2).reshape(nq, total)
+    want_i, want_d = mdist.merge_topk(flat_i, flat_d, k_out)
+    assert torch.equal(got_i, want_i) and torch.equal(got_d, want_d)
