@@ -88,7 +88,7 @@ def sharded_exact_search(local_search, queries, k, group=None, merge=None):
     """`local_search(queries, k)` -> this rank's (ids, dists) with GLOBAL internal ids, sorted under the
     reference order.  Returns the merged global (ids, dists), identical on every rank.  On the GPU the
     lists are gathered as [world x nq x k] and merged by rank counting (morna_merge_sorted_topk); a
-    `merge(ids [nq x world*k], dists, k)` callable replaces that (CPU tests pass the oracle's rule)."""
+    `merge(ids [nq x world*k], dists, k)` callable replaces that (the CPU tests pass their own reference rule)."""
     import torch.distributed as td
     ids, dists = local_search(queries, k)
     if not (td.is_available() and td.is_initialized() and td.get_world_size(group) > 1):
