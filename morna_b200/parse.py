@@ -118,8 +118,7 @@ def tokenize_buffer(buf, n_threads=None):
     return keys[:kb], key_off, row_off, sample[:pr], cov[:pr], line_off, needs[:n]
 
 
-def read_blocks(fh, block_bytes=64 << 20):
-    """Binary file object -> bytes blocks ending at a line boundary."""
+def _read_blocks_sync(fh, block_bytes):
     tail = b""
     while True:
         chunk = fh.read(block_bytes)
@@ -133,6 +132,39 @@ def read_blocks(fh, block_bytes=64 << 20):
             continue
         yield tail + chunk[:cut + 1]
         tail = chunk[cut + 1:]
+
+
+def read_blocks(fh, block_bytes=32 << 20, prefetch=2):
+    """Binary file object -> bytes blocks ending at a line boundary.  A reader thread stays ``prefetch``
+    blocks ahead (zlib releases the GIL), so gunzip overlaps the tokenising and bookkeeping of the
+    previous block -- gunzip is the slowest stage of an index build end to end."""
+    if prefetch <= 0:
+        for block in _read_blocks_sync(fh, block_bytes):
+            yield block
+        return
+    import queue
+    import threading
+    q = queue.Queue(maxsize=prefetch)
+    done = object()
+
+    def reader():
+        try:
+            for block in _read_blocks_sync(fh, block_bytes):
+                q.put(block)
+            q.put(done)
+        except BaseException as exc:            # surface read errors in the consumer
+            q.put(exc)
+
+    t = threading.Thread(target=reader, daemon=True)
+    t.start()
+    while True:
+        item = q.get()
+        if item is done:
+            break
+        if isinstance(item, BaseException):
+            raise item
+        yield item
+    t.join()
 
 
 def open_intropolis_binary(path):
