@@ -539,17 +539,27 @@ kth_warp_kernel(KthParams p, int nq) {
         // stream: lane owns float4 groups lane, lane+32, ...; survivors go to its private list
         const int groups = (count + 3) >> 2;
         bool overflowed = false;
-        for (int g = lane; g < groups; g += 32) {
-            float4 v = *reinterpret_cast<const float4 *>(src + 4 * g);      // rows are 16-byte aligned and padded
-            const float vv[4] = {v.x, v.y, v.z, v.w};
+        for (int g0 = lane; g0 < groups; g0 += 32 * 4) {                     // four 16-byte loads in flight per lane
+            float4 v[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int idx = 4 * g + t;
-                const uint32_t key = float_key(vv[t]);
-                if (idx < count && key >= pivot) {
-                    if (mine < kKwSlots) { lkey[mine * 32 + lane] = key; lidx[mine * 32 + lane] = idx; }
-                    else overflowed = true;
-                    ++mine;
+            for (int u = 0; u < 4; ++u) {
+                const int g = g0 + 32 * u;
+                v[u] = g < groups ? *reinterpret_cast<const float4 *>(src + 4 * g)   // rows are 16-byte aligned and padded
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int g = g0 + 32 * u;
+                const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int idx = 4 * g + t;
+                    const uint32_t key = float_key(vv[t]);
+                    if (idx < count && key >= pivot) {
+                        if (mine < kKwSlots) { lkey[mine * 32 + lane] = key; lidx[mine * 32 + lane] = idx; }
+                        else overflowed = true;
+                        ++mine;
+                    }
                 }
             }
         }
@@ -858,6 +868,7 @@ static int g_gemm_stages = 4;
 static int g_block_rows = 131072;  // rows scored between two refinements of the candidate lists (key 9)
 static int g_pilot_rows = kKthMax; // rows of the pilot block whose scores are dumped for the first thresholds (key 10)
 static int g_first_block = 0;      // rows up to the first refinement (key 11); 0 = g_block_rows
+static int g_rerank_ctas_per_sm = 0; // key 13: cap on resident re-rank CTAs per SM (0 = whatever fits)
 static int g_rerank_rows = 8;     // candidate rows per warp pass of the re-rank (2, 4 or 8)
 static int g_rerank_phase_mb = 0;  // row range kept L2-resident per re-rank phase; 0 = never split into phases
 
@@ -1085,6 +1096,7 @@ extern "C" int morna_knn_batched_rerank(const float *vectors, const double *pp, 
     int per_sm = 0;
     MORNA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRrThreads, rr_smem));
     if (per_sm < 1) per_sm = 1;
+    if (g_rerank_ctas_per_sm > 0 && per_sm > g_rerank_ctas_per_sm) per_sm = g_rerank_ctas_per_sm;
     const int64_t items = (int64_t)nq * rp.phases;
     int64_t rr_grid = (int64_t)per_sm * sm_count_b();
     if (rr_grid > items) rr_grid = items;
@@ -1154,6 +1166,7 @@ extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
     else if (key == 4) morna::set_acc_pipelined(value);
     else if (key == 1) g_gemm_stages = value;
     else if (key == 5) g_rerank_rows = value;
+    else if (key == 13) g_rerank_ctas_per_sm = value;
     else if (key == 9) g_block_rows = value >= 256 ? value : 131072;
     else if (key == 10) g_pilot_rows = value >= 256 && value <= kPilotMax ? value : kPilotMax;
     else if (key == 11) g_first_block = value > 0 ? value : 0;
