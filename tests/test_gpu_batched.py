@@ -279,3 +279,21 @@ def test_headline_shape_properties():
         parts.append(sh.batched_search_device(q[pick], k))
     m_ids, m_d = mdist.merge_topk(torch.cat([p[0] for p in parts], 1), torch.cat([p[1] for p in parts], 1), k)
     assert torch.equal(m_ids, ids[pick]) and torch.equal(m_d, dist[pick])
+
+
+@pytest.mark.parametrize("k", [1, 257, 512])
+def test_large_and_small_k_on_every_path(k):
+    rng = np.random.default_rng(k)
+    n, d, nq = 12000, 160, 150
+    S = rng.standard_normal((n, d)).astype(np.float32)
+    srch = make_search(S)
+    Q = S[rng.permutation(n)[:nq]].astype(np.float64) + 0.03 * rng.standard_normal((nq, d))
+    q = torch.from_numpy(Q).cuda()
+    e_ids, e_d = srch.exact_search_device(q, k, allow_single=False)
+    b_ids, b_d = srch.batched_search_device(q, k)
+    assert torch.equal(b_ids, e_ids) and torch.equal(b_d, e_d)
+    for j in (0, 77):
+        s_ids, s_d = srch.single_search_device(q[j], k)
+        assert torch.equal(s_ids[0], e_ids[j]) and torch.equal(s_d[0], e_d[j])
+    true_d = c_oracle.distances(S, Q[3])
+    check_topk(true_d, b_ids[3].cpu().numpy(), b_d[3].cpu().numpy(), tol=1e-9)
