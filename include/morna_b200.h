@@ -251,8 +251,14 @@ int morna_debug_tensor_scores(const void *hs, int64_t ld_h, const float *rho_max
                               int64_t scores_ld, float *eps_out, void *workspace, size_t workspace_bytes,
                               void *stream);
 
-/* Experiment knobs (process-wide; not part of the drop-in surface): key 0 = GEMM variant
- * (1 = CTA pairs with cta_group::2, 0 = single CTAs), key 1 = pipeline stages (4 or 6). */
+/* Experiment knobs (process-wide; not part of the drop-in surface; every setting returns the same results):
+ *   0  GEMM variant (1 = CTA pairs with cta_group::2, 0 = single CTAs)      1  GEMM pipeline stages (4 or 6)
+ *   3  single query: rows per warp pass (1..5, 0 = automatic)               4  index: pipelined barrier-per-row kernel (1) or the simple one (0)
+ *   5  re-rank: candidate rows per warp pass (2, 4, 8)                       6  re-rank: MB of rows per L2 phase (0 = no phases)
+ *   7  index: id tiles per bucket column of the barrier-per-row kernel      8  index: 3 = warp-per-range kernel when it pays, 4 = always, 0 = never
+ *   9  batched: rows scored between threshold refinements (default 131072)  10 batched: pilot rows (256..8192)
+ *   11 batched: rows before the first refinement (0 = key 9's value)        12 index: log2 width of the sample-id ranges (10..12)
+ *   13 re-rank: cap on resident CTAs per SM (0 = whatever fits) */
 int morna_debug_set_tuning(int32_t key, int32_t value);
 
 #ifdef __cplusplus
