@@ -119,7 +119,7 @@ int morna_tokenize_fill(const char *text, size_t nbytes, int32_t n_threads, uint
  *   id_of_sample     [dev] int32[max_sample_id + 1] from morna_assign_internal_ids
  *   acc              [dev] double[dim * acc_ld], acc_ld >= id_hi - id_lo
  */
-size_t morna_index_accumulate_workspace_bytes(int64_t n_rows, int32_t dim);
+size_t morna_index_accumulate_workspace_bytes(int64_t n_rows, int64_t nnz, int32_t dim);
 int morna_index_accumulate(const int64_t *row_off, const uint8_t *pass, const int32_t *bucket,
                            const int8_t *sign, const double *idf, int64_t n_rows,
                            const int32_t *sample, const int32_t *cov, int64_t nnz,

@@ -36,7 +36,7 @@ _SIGNATURES = {
                                                  _c_vp, _c_sz, _c_vp]),
     "morna_tokenize_count": (ctypes.c_int, [_c_vp, _c_sz, _c_i32, _c_vp, _c_vp, _c_vp]),
     "morna_tokenize_fill": (ctypes.c_int, [_c_vp, _c_sz, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
-    "morna_index_accumulate_workspace_bytes": (_c_sz, [_c_i64, _c_i32]),
+    "morna_index_accumulate_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_i32]),
     "morna_index_accumulate": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64,
                                               _c_vp, _c_i32, _c_i32, _c_i32, _c_i32, _c_vp, _c_i64, _c_vp, _c_sz, _c_vp]),
     "morna_round_store": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_i32, _c_vp, _c_i64, _c_vp]),

@@ -212,11 +212,62 @@ sorted_row_len_kernel(const int32_t *__restrict__ use_flag, const int64_t *__res
     }
 }
 
+// Streaming form of the "every row ascends" question, position-parallel instead of warp-per-row: a bit per
+// pair position marks the row starts, then every pair is compared with its predecessor unless it starts a row.
+// (All rows are checked, also those under the threshold: a stray descending row there only costs the fast path.)
+__global__ void __launch_bounds__(256)
+row_start_bits_kernel(const int64_t *__restrict__ row_off, int64_t n_rows, int64_t nnz, uint32_t *__restrict__ bits) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_rows; j += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = row_off[j];
+        if (p < nnz && row_off[j + 1] > p) atomicOr(bits + (p >> 5), 1u << (p & 31));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pairs_ascending_kernel(const int32_t *__restrict__ sample, int64_t nnz, const uint32_t *__restrict__ bits,
+                       int32_t *__restrict__ not_ascending) {
+    // thread = 4 consecutive positions (one 16-byte load) plus the element before them; four such groups in flight
+    const int64_t groups = nnz >> 2;                           // whole groups; the tail is checked by thread 0
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g0 < groups; g0 += 4 * stride) {
+        int4 v[4];
+        int32_t prev[4];
+        uint32_t word[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t g = g0 + u * stride;
+            const bool have = g < groups;
+            v[u] = have ? __ldg(reinterpret_cast<const int4 *>(sample) + g) : make_int4(0, 1, 2, 3);
+            prev[u] = have && g > 0 ? __ldg(sample + 4 * g - 1) : -1;
+            word[u] = have ? __ldg(bits + (g >> 3)) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t g = g0 + u * stride;
+            const uint32_t start = (word[u] >> ((4 * g) & 31)) & 0xfu;     // row-start flags of the four positions
+            bad |= !(start & 1u) && v[u].x <= prev[u];
+            bad |= !(start & 2u) && v[u].y <= v[u].x;
+            bad |= !(start & 4u) && v[u].z <= v[u].y;
+            bad |= !(start & 8u) && v[u].w <= v[u].z;
+            bad |= (v[u].x | v[u].y | v[u].z | v[u].w) < 0;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t p = 4 * groups; p < nnz; ++p) {
+            const bool start = (bits[p >> 5] >> (p & 31)) & 1u;
+            bad |= sample[p] < 0 || (!start && p > 0 && sample[p] <= sample[p - 1]);
+        }
+    if (bad) *not_ascending = 1;
+}
+
 // rows whose sample ids are strictly increasing or strictly decreasing cannot list a sample twice;
 // flags[0] = some passing row is neither, flags[1] = some passing row is not strictly increasing
 __global__ void __launch_bounds__(256)
-rows_monotonic_kernel(const int64_t *__restrict__ row_off, const uint8_t *__restrict__ pass, int64_t n_rows,
-                      const int32_t *__restrict__ sample, int32_t *__restrict__ flags) {
+rows_monotonic_kernel(const int32_t *__restrict__ use_flag, const int64_t *__restrict__ row_off,
+                      const uint8_t *__restrict__ pass, int64_t n_rows, const int32_t *__restrict__ sample,
+                      int32_t *__restrict__ flags) {
+    if (use_flag && !*use_flag) return;      // every row ascends: nothing to classify
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n_rows; j += warps_total) {
@@ -403,22 +454,59 @@ row_segments_kernel(const int64_t *__restrict__ row_off, const int8_t *__restric
     }
 }
 
-struct WarpMeta { double w[32]; int32_t pos[32]; int32_t n[32]; };      // one batch of 32 rows, this warp's range
-struct WarpSlots { double w[2][kAcc3Group]; };                           // +-idf of the chunks in flight
+// A chunk: up to 32 consecutive pairs of one row that fall in one sample-id range.
+struct __align__(16) ChunkDesc { int32_t pos; int32_t cnt_end; double w; };   // first pair, pairs | last-of-row << 8, +-idf
 
-// One warp = (bucket, sample-id range): the bucket's rows in file order, for each row the pairs whose
-// sample id falls in the range.  The work is cut into chunks of up to 32 consecutive pairs of one
-// row (a row's segment of n pairs is ceil(n/32) chunks; an empty segment is none); a uniform software
-// pipeline keeps the loads of the next eight chunks in flight while the current eight are added, and
-// the rows' metadata is fetched one batch of 32 rows ahead.  A __syncwarp() follows the last chunk of
-// each row, so rows are applied in file order; the chunks of one row hold distinct samples.  Runs only
-// if rows_monotonic_kernel found every passing row strictly ascending (otherwise the binary-searched
-// segments mean nothing and the barrier-per-row variants do the work).
+// chunks per (range, sorted row), range-major so that one exclusive scan gives every (bucket, range) list
+// its place:  cnt[p * n_pass + r] = ceil(n / 32), n = pairs of row r in range p
+__global__ void __launch_bounds__(256)
+chunk_count_kernel(const int32_t *__restrict__ seg, const int32_t *__restrict__ bucket_begin, int32_t dim,
+                   int32_t n_ranges, int64_t n_rows_cap, int32_t *__restrict__ cnt) {
+    const int64_t n_pass = bucket_begin[dim];
+    const int64_t total = n_pass * n_ranges;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n_rows_cap * n_ranges; i += (int64_t)gridDim.x * blockDim.x) {
+        int32_t c = 0;
+        if (i < total) {
+            const int64_t p = i / n_pass, r = i - p * n_pass;
+            const int32_t *sg = seg + r * (n_ranges + 1) + p;
+            c = (max(sg[1] - sg[0], 0) + 31) >> 5;
+        }
+        cnt[i] = c;                                            // zeros past the passing rows: the scan covers the whole array
+    }
+}
+
+__global__ void __launch_bounds__(256)
+chunk_fill_kernel(const int32_t *__restrict__ seg, const RowMeta *__restrict__ meta, const int32_t *__restrict__ bucket_begin,
+                  int32_t dim, int32_t n_ranges, const int32_t *__restrict__ chunk_off, ChunkDesc *__restrict__ desc) {
+    const int64_t n_pass = bucket_begin[dim];
+    const int64_t total = n_pass * n_ranges;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i / n_pass, r = i - p * n_pass;
+        const int32_t *sg = seg + r * (n_ranges + 1) + p;
+        const int32_t lo = sg[0], n = max(sg[1] - lo, 0);
+        if (n == 0) continue;
+        const RowMeta mt = meta[r];
+        const int32_t pos0 = (int32_t)mt.pos + lo;             // nnz < 2^31 (checked by the host entry)
+        ChunkDesc *out = desc + chunk_off[i];
+        for (int32_t c = 0; c < n; c += 32) {
+            ChunkDesc d;
+            d.pos = pos0 + c; d.cnt_end = min(32, n - c) | ((c + 32 >= n) << 8); d.w = mt.w;
+            *out++ = d;
+        }
+    }
+}
+
+// One warp = (bucket, sample-id range).  Its work arrives as a ready-made list of chunks in file order
+// (chunk_fill_kernel): the warp streams the list -- descriptors 32 at a time through a two-slot ring in
+// shared memory, the pairs of the next eight chunks in flight while the current eight are added -- and a
+// __syncwarp() follows the last chunk of each row, so rows are applied in file order; the chunks of one
+// row hold distinct samples.  Every cell sees its addends in the reference's order (morna.py:376-388).
+// Runs only if rows_monotonic_kernel found every passing row strictly ascending.
 __global__ void __launch_bounds__(kAcc3Threads)
 index_accumulate3_kernel(const int32_t *__restrict__ not_ascending, const int32_t *__restrict__ sample,
                          const int32_t *__restrict__ cov, const int32_t *__restrict__ id_of_sample,
-                         const int32_t *__restrict__ bucket_begin, const int32_t *__restrict__ seg,
-                         const RowMeta *__restrict__ meta, int32_t shift, int32_t n_ranges, int32_t max_sample_id,
+                         const int32_t *__restrict__ bucket_begin, int32_t dim, const int32_t *__restrict__ chunk_off,
+                         const ChunkDesc *__restrict__ desc, int32_t shift, int32_t n_ranges, int32_t max_sample_id,
                          int32_t id_lo, int32_t id_hi, double *__restrict__ acc, int64_t acc_ld) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (*not_ascending) return;                                // the order-by-barrier variants run instead
@@ -428,84 +516,60 @@ index_accumulate3_kernel(const int32_t *__restrict__ not_ascending, const int32_
     if (range >= n_ranges) return;                             // no block-wide barrier below
     const int32_t width = 1 << shift, range_lo = range << shift;
     double *slice = reinterpret_cast<double *>(smem_raw) + (size_t)warp * width;
-    unsigned char *after = smem_raw + (size_t)kAcc3Warps * width * sizeof(double);
-    WarpMeta *wm = reinterpret_cast<WarpMeta *>(after) + 2 * warp;
-    WarpSlots *ws = reinterpret_cast<WarpSlots *>(after + (size_t)kAcc3Warps * 2 * sizeof(WarpMeta)) + warp;
-    const int32_t r_begin = bucket_begin[b], r_end = bucket_begin[b + 1];
-    const int nrows = r_end - r_begin;
-    if (nrows == 0) return;                                    // acc was zero-filled by the caller
+    ChunkDesc *ring = reinterpret_cast<ChunkDesc *>(smem_raw + (size_t)kAcc3Warps * width * sizeof(double)) + 64 * warp;
+    const int64_t n_pass = bucket_begin[dim];
+    const int32_t d_begin = chunk_off[(int64_t)range * n_pass + bucket_begin[b]];
+    const int32_t d_end = chunk_off[(int64_t)range * n_pass + bucket_begin[b + 1]];
+    const int n_chunks = d_end - d_begin;
+    if (bucket_begin[b] == bucket_begin[b + 1]) return;        // acc was zero-filled by the caller
     for (int i = lane; i < width; i += 32) slice[i] = 0.0;
-    const int n_batches = (nrows + 31) / 32;
+    const int n_groups = (n_chunks + kAcc3Group - 1) / kAcc3Group;
+    const ChunkDesc *list = desc + d_begin;
 
-    // this lane's row of a metadata batch -> registers; published to shared memory when the cursor reaches the batch
-    int32_t a_pos = 0, a_n = 0;
-    double a_w = 0.0;
-    auto fetch_meta = [&](int batch) {
-        const int32_t r = r_begin + 32 * batch + lane;
-        a_pos = 0; a_n = 0; a_w = 0.0;
-        if (batch < n_batches && r < r_end) {
-            const int32_t *sg = seg + (int64_t)r * (n_ranges + 1) + range;
-            const int32_t lo = sg[0], hi = sg[1];
-            const RowMeta mt = meta[r];
-            a_pos = (int32_t)mt.pos + lo; a_n = max(hi - lo, 0); a_w = mt.w;    // nnz < 2^31 (checked by the host entry)
-        }
+    // descriptors: this lane's entry of a batch of 32 -> registers, published to the ring when the batch is reached
+    int4 pending = make_int4(0, 0, 0, 0);
+    auto fetch_batch = [&](int batch) {
+        const int i = 32 * batch + lane;
+        pending = i < n_chunks ? __ldg(reinterpret_cast<const int4 *>(list + i)) : make_int4(0, 0, 0, 0);
     };
-    auto publish_meta = [&](int batch) {
-        __syncwarp();                                          // nobody still reads the buffer being replaced
-        WarpMeta &m = wm[batch & 1];
-        m.pos[lane] = a_pos; m.n[lane] = a_n; m.w[lane] = a_w;
+    auto publish_batch = [&](int batch) {
+        __syncwarp();                                          // nobody still reads the slot being replaced
+        reinterpret_cast<int4 *>(ring + 32 * (batch & 1))[lane] = pending;
         __syncwarp();
     };
-    // cursor over the chunk stream: row cur_r (relative to r_begin), offset cur_c into its segment
-    int cur_r = -1, cur_c = 0, cur_n = 0, cur_pos = 0;
-    double cur_w = 0.0;
-    // fills one group: descriptors (pairs in the chunk | last-of-row flag << 8; 0 = no chunk) and the loads
-    auto issue = [&](int buf, int32_t (&desc)[kAcc3Group], int32_t (&ps)[kAcc3Group], int32_t (&pc)[kAcc3Group]) {
-        bool any = false;
+    auto issue = [&](int g, int32_t (&ps)[kAcc3Group], int32_t (&pc)[kAcc3Group]) {
+        if ((g & 3) == 0) { publish_batch(g >> 2); fetch_batch((g >> 2) + 1); }
+        const ChunkDesc *slot = ring + 32 * ((g >> 2) & 1) + (g & 3) * kAcc3Group;
 #pragma unroll
         for (int u = 0; u < kAcc3Group; ++u) {
-            while (cur_r < nrows && cur_c >= cur_n) {          // next row with pairs left in this range
-                ++cur_r; cur_c = 0;
-                if (cur_r < nrows) {
-                    if ((cur_r & 31) == 0) { publish_meta(cur_r >> 5); fetch_meta((cur_r >> 5) + 1); }
-                    const WarpMeta &m = wm[(cur_r >> 5) & 1];
-                    cur_n = m.n[cur_r & 31]; cur_pos = m.pos[cur_r & 31]; cur_w = m.w[cur_r & 31];
-                } else cur_n = 0;
-            }
-            desc[u] = 0; ps[u] = -1; pc[u] = 0;
-            if (cur_r < nrows) {
-                const int32_t cnt = min(32, cur_n - cur_c);
-                if (lane < cnt) { ps[u] = __ldg(sample + cur_pos + cur_c + lane); pc[u] = __ldg(cov + cur_pos + cur_c + lane); }
-                cur_c += cnt;
-                desc[u] = cnt | ((cur_c >= cur_n) << 8);
-                if (lane == 0) ws->w[buf][u] = cur_w;
-                any = true;
-            }
+            const int2 pc2 = *reinterpret_cast<const int2 *>(slot + u);        // pos, cnt_end (broadcast read)
+            const bool have = lane < (pc2.y & 0xff);
+            ps[u] = have ? __ldg(sample + pc2.x + lane) : -1;
+            pc[u] = have ? __ldg(cov + pc2.x + lane) : 0;
         }
-        __syncwarp();
-        return any;
     };
-    auto apply = [&](int buf, const int32_t (&desc)[kAcc3Group], const int32_t (&ps)[kAcc3Group], const int32_t (&pc)[kAcc3Group]) {
+    auto apply = [&](int g, const int32_t (&ps)[kAcc3Group], const int32_t (&pc)[kAcc3Group]) {
+        const ChunkDesc *slot = ring + 32 * ((g >> 2) & 1) + (g & 3) * kAcc3Group;
 #pragma unroll
         for (int u = 0; u < kAcc3Group; ++u) {
-            if (desc[u] == 0) break;
+            const ChunkDesc d = slot[u];
             if (ps[u] >= 0) {
                 double *cell = slice + (ps[u] - range_lo);
-                *cell = __dadd_rn(*cell, __dmul_rn((double)pc[u], ws->w[buf][u]));   // product rounded, then added: as the reference
+                *cell = __dadd_rn(*cell, __dmul_rn((double)pc[u], d.w));        // product rounded, then added: as the reference
             }
-            if (desc[u] >> 8) __syncwarp();                    // the row is complete: rows are applied in file order
+            if (d.cnt_end >> 8) __syncwarp();                  // the row is complete: rows are applied in file order
         }
     };
 
-    fetch_meta(0);
-    int32_t da[kAcc3Group], sa[kAcc3Group], ca[kAcc3Group], db[kAcc3Group], sb[kAcc3Group], cb[kAcc3Group];
-    bool more = issue(0, da, sa, ca);
-    while (more) {
-        const bool more_b = issue(1, db, sb, cb);              // next group's loads fly during this group's adds
-        apply(0, da, sa, ca);
-        if (!more_b) break;
-        more = issue(0, da, sa, ca);
-        apply(1, db, sb, cb);
+    fetch_batch(0);
+    int32_t sa[kAcc3Group], ca[kAcc3Group], sb[kAcc3Group], cb[kAcc3Group];
+    if (n_groups > 0) issue(0, sa, ca);
+    for (int g = 0; g < n_groups; g += 2) {
+        if (g + 1 < n_groups) issue(g + 1, sb, cb);            // next group's loads fly during this group's adds
+        apply(g, sa, ca);
+        if (g + 1 >= n_groups) break;
+        if (g + 2 < n_groups) issue(g + 2, sa, ca);
+        apply(g + 1, sb, cb);
     }
     __syncwarp();
     // the slice is in sample-id order; the accumulator is indexed by internal id
@@ -559,8 +623,9 @@ static IdsWs ids_ws_layout(int64_t m) {
 }
 
 constexpr int kAcc3MaxRanges = 32;
-struct AccWs { size_t keys_in, keys_out, vals_in, vals_out, begin, cub, cub_bytes, len, voff, scan, scan_bytes, flag, seg, meta, total; };
-static AccWs acc_ws_layout(int64_t n_rows, int32_t dim) {
+struct AccWs { size_t keys_in, keys_out, vals_in, vals_out, begin, cub, cub_bytes, len, voff, scan, scan_bytes, flag, seg, meta,
+               ccnt, coff, cscan, cscan_bytes, desc, bits, total; };
+static AccWs acc_ws_layout(int64_t n_rows, int64_t nnz, int32_t dim) {
     AccWs w{};
     size_t off = 0;
     w.keys_in = off; off += align_up((size_t)n_rows * 4, 256);
@@ -580,6 +645,15 @@ static AccWs acc_ws_layout(int64_t n_rows, int32_t dim) {
     w.flag = off; off += 256;
     w.seg = off; off += align_up((size_t)n_rows * (kAcc3MaxRanges + 1) * 4, 256);
     w.meta = off; off += align_up((size_t)n_rows * sizeof(RowMeta), 256);
+    // chunk lists of the warp-per-range variant: counts and offsets per (range, row), descriptors
+    const size_t cells = (size_t)n_rows * kAcc3MaxRanges + 1;
+    w.ccnt = off; off += align_up(cells * 4, 256);
+    w.coff = off; off += align_up(cells * 4, 256);
+    size_t cscan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, cscan_bytes, (const int32_t *)nullptr, (int32_t *)nullptr, (int)cells);
+    w.cscan = off; w.cscan_bytes = cscan_bytes; off += align_up(cscan_bytes, 256);
+    w.desc = off; off += align_up(((size_t)(nnz > 0 ? nnz : 0) / 32 + cells) * sizeof(ChunkDesc), 256);
+    w.bits = off; off += align_up(((size_t)(nnz > 0 ? nnz : 0) / 32 + 2) * 4, 256);
     w.total = off + 256;
     return w;
 }
@@ -680,9 +754,9 @@ extern "C" int morna_assign_internal_ids(const int64_t *row_off, const uint8_t *
     return MORNA_OK;
 }
 
-extern "C" size_t morna_index_accumulate_workspace_bytes(int64_t n_rows, int32_t dim) {
+extern "C" size_t morna_index_accumulate_workspace_bytes(int64_t n_rows, int64_t nnz, int32_t dim) {
     if (n_rows < 0 || dim <= 0) return 256;
-    return acc_ws_layout(n_rows, dim).total;
+    return acc_ws_layout(n_rows, nnz, dim).total;
 }
 
 extern "C" int morna_index_accumulate(const int64_t *row_off, const uint8_t *pass, const int32_t *bucket,
@@ -695,7 +769,7 @@ extern "C" int morna_index_accumulate(const int64_t *row_off, const uint8_t *pas
         max_sample_id < 0 || dim <= 0 || id_lo < 0 || id_hi < id_lo || acc_ld < (int64_t)(id_hi - id_lo) || n_rows > 0x7fffffff)
         return MORNA_ERR_INVALID_ARGUMENT;
     if (nnz > 0 && (!sample || !cov)) return MORNA_ERR_INVALID_ARGUMENT;
-    AccWs w = acc_ws_layout(n_rows, dim);
+    AccWs w = acc_ws_layout(n_rows, nnz, dim);
     if (!workspace || workspace_bytes < w.total) return MORNA_ERR_WORKSPACE_TOO_SMALL;
     cudaStream_t s = (cudaStream_t)stream;
     MORNA_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)dim * (size_t)acc_ld * sizeof(double), s));
@@ -719,12 +793,20 @@ extern "C" int morna_index_accumulate(const int64_t *row_off, const uint8_t *pas
     auto *flag = (int32_t *)(ws + w.flag);                 // [0] a row repeats a sample, [1] a row is not ascending
     MORNA_CUDA_TRY(cudaMemsetAsync(flag, 0, 2 * sizeof(int32_t), s));
     const int32_t *use_old = nullptr;                      // nullptr: the barrier-per-row variants run unconditionally
-    rows_monotonic_kernel<<<grid_for(n_rows * 32, 256), 256, 0, s>>>(row_off, pass, n_rows, sample, flag);
-    MORNA_LAUNCH_CHECK();
     // few rows per bucket (very wide --features): the per-(bucket, range) set-up of the warp variant is not
     // amortised and the barrier-per-row variants are faster (measured: 30,000 features over 1.1 M rows)
     const bool enough_rows = g_acc_variant == 4 || n_rows / dim >= 64 || n_rows < 4096;
     if ((g_acc_variant == 3 || g_acc_variant == 4) && enough_rows && nnz < 0x7fffffff) {
+        auto *bits = (uint32_t *)(ws + w.bits);
+        MORNA_CUDA_TRY(cudaMemsetAsync(bits, 0, ((size_t)nnz / 32 + 2) * 4, s));
+        row_start_bits_kernel<<<grid_for(n_rows, 256), 256, 0, s>>>(row_off, n_rows, nnz, bits);
+        MORNA_LAUNCH_CHECK();
+        if (((uintptr_t)sample & 15) == 0) {
+            pairs_ascending_kernel<<<grid_for(nnz / 16 + 1, 256), 256, 0, s>>>(sample, nnz, bits, flag + 1);
+        } else {                                               // (16-byte loads need an aligned array)
+            rows_monotonic_kernel<<<grid_for(n_rows * 32, 256), 256, 0, s>>>(nullptr, row_off, pass, n_rows, sample, flag);
+        }
+        MORNA_LAUNCH_CHECK();
         // sample-id ranges of 2^shift ids, at most kAcc3MaxRanges of them, at least 1024 ids wide
         int32_t shift = g_acc_shift;
         while (((int64_t)max_sample_id >> shift) + 1 > kAcc3MaxRanges) ++shift;
@@ -734,12 +816,23 @@ extern "C" int morna_index_accumulate(const int64_t *row_off, const uint8_t *pas
         row_segments_kernel<<<grid_for(n_rows * (n_ranges + 1), 256), 256, 0, s>>>(row_off, sign, idf, sample, vals_out, begin,
                                                                                  dim, shift, n_ranges, seg, meta);
         MORNA_LAUNCH_CHECK();
-        const size_t smem3 = (size_t)kAcc3Warps * (((size_t)1 << shift) * sizeof(double) + 2 * sizeof(WarpMeta) + sizeof(WarpSlots));
-        if (smem3 <= 200 * 1024) {
+        const size_t smem3 = (size_t)kAcc3Warps * (((size_t)1 << shift) * sizeof(double) + 64 * sizeof(ChunkDesc));
+        if (smem3 <= 200 * 1024 && (int64_t)n_rows * n_ranges < 0x7fffffff) {
+            auto *ccnt = (int32_t *)(ws + w.ccnt);
+            auto *coff = (int32_t *)(ws + w.coff);
+            auto *desc = (ChunkDesc *)(ws + w.desc);
+            const int64_t cells = (int64_t)n_rows * n_ranges + 1;
+            chunk_count_kernel<<<grid_for(cells, 256), 256, 0, s>>>(seg, begin, dim, n_ranges, n_rows, ccnt);
+            MORNA_LAUNCH_CHECK();
+            size_t cscan_bytes = w.cscan_bytes;
+            MORNA_CUDA_TRY(cub::DeviceScan::ExclusiveSum(ws + w.cscan, cscan_bytes, ccnt, coff, (int)cells, s));
+            count_launch(2);
+            chunk_fill_kernel<<<grid_for(cells, 256), 256, 0, s>>>(seg, meta, begin, dim, n_ranges, coff, desc);
+            MORNA_LAUNCH_CHECK();
             MORNA_CUDA_TRY(cudaFuncSetAttribute(index_accumulate3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
             dim3 grid3((unsigned)dim, (unsigned)((n_ranges + kAcc3Warps - 1) / kAcc3Warps));
-            index_accumulate3_kernel<<<grid3, kAcc3Threads, smem3, s>>>(flag + 1, sample, cov, id_of_sample, begin, seg, meta, shift,
-                                                                      n_ranges, max_sample_id, id_lo, id_hi, acc, acc_ld);
+            index_accumulate3_kernel<<<grid3, kAcc3Threads, smem3, s>>>(flag + 1, sample, cov, id_of_sample, begin, dim, coff, desc,
+                                                                      shift, n_ranges, max_sample_id, id_lo, id_hi, acc, acc_ld);
             MORNA_LAUNCH_CHECK();
             use_old = flag + 1;                            // the variants below run only if a row was not ascending
         }
@@ -763,6 +856,8 @@ extern "C" int morna_index_accumulate(const int64_t *row_off, const uint8_t *pas
             MORNA_CUDA_TRY(cudaFuncSetAttribute(index_accumulate2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)(kAcc2Tile * sizeof(double) + kAcc2MetaBytes)));
         }
+        rows_monotonic_kernel<<<grid_for(n_rows * 32, 256), 256, 0, s>>>(use_old, row_off, pass, n_rows, sample, flag);
+        MORNA_LAUNCH_CHECK();
         dim3 grid2((unsigned)dim, (unsigned)tiles2);
         index_accumulate2_kernel<false><<<grid2, kAcc2Threads, smem2, s>>>(use_old, flag, row_off, sign, idf, sample, cov, id_of_sample,
                                                                          vals_out, begin, voff, id_lo, id_hi, tile2, acc, acc_ld);

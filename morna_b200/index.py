@@ -185,7 +185,7 @@ class MornaIndex(object):
             width = max(hi - lo, 0)
             acc_ld = max(round_up(width, 32), 32)
             d_acc = torch.empty(self.dim * acc_ld, dtype=torch.float64, device=dev)
-            ws = _lib.workspace(lib.morna_index_accumulate_workspace_bytes(n_rows, self.dim), dev)
+            ws = _lib.workspace(lib.morna_index_accumulate_workspace_bytes(n_rows, nnz, self.dim), dev)
             _lib.check(lib.morna_index_accumulate(
                 _lib.dev_ptr(d_row_off), _lib.dev_ptr(d_pass), _lib.dev_ptr(d_bucket), _lib.dev_ptr(d_sign),
                 _lib.dev_ptr(d_idf), n_rows, _lib.dev_ptr(d_sample), _lib.dev_ptr(d_cov), nnz,

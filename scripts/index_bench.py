@@ -85,7 +85,7 @@ for dim in [int(x) for x in args.dims.split(",")]:
                    _lib.dev_ptr(d_bucket), _lib.dev_ptr(d_sign), sp), "hash"))
     acc_ld = (n_kept + 31) // 32 * 32
     d_acc = torch.empty(dim * acc_ld, dtype=torch.float64, device=dev)
-    ws_acc = _lib.workspace(lib.morna_index_accumulate_workspace_bytes(J, dim), dev)
+    ws_acc = _lib.workspace(lib.morna_index_accumulate_workspace_bytes(J, nnz, dim), dev)
     for split in [int(x) for x in args.splits.split(",") if x]:
         lib.morna_debug_set_tuning(12, split)
         t_s = timed(lambda: _lib.check(lib.morna_index_accumulate(_lib.dev_ptr(d_row_off), _lib.dev_ptr(d_pass), _lib.dev_ptr(d_bucket), _lib.dev_ptr(d_sign),
