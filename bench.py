@@ -386,7 +386,26 @@ def dominant_kernel_roofline(torch, lib, _lib, srch, queries64, peaks):
               "traffic": rr_traffic, "launch_ms": acc[5],
               "algorithmic": "candidates * 4 * ld bytes gathered per batch (%d candidates x %d B); rows re-ranked by several "
                              "queries hit in L2, so achieved can exceed the DRAM traffic rate" % (srch.last_stats[2] // blocks, srch.ld * 4)}
+    # context only (not on the product path): the same contraction through cuBLAS, fp16 in / fp16 out
+    lib_ms = None
+    try:
+        a16 = torch.randn((nq, ld_h), device=queries64.device, dtype=torch.float16)
+        b16 = srch.hs[n_all - rows:n_all]
+        out16 = torch.empty((nq, rows), device=queries64.device, dtype=torch.float16)
+        for _ in range(3):
+            torch.matmul(a16, b16.t(), out=out16)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        for _ in range(10):
+            e0.record(); torch.matmul(a16, b16.t(), out=out16); e1.record(); torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1) / 10
+        lib_ms = tot
+        del a16, out16
+    except Exception:
+        pass
     return {"bound": "tensor", "kernel": "knn_gemm2_kernel<4> (tcgen05 cta_group::2 fp16 UMMA, filter pass over %d rows)" % rows,
+            "cublas_same_shape": None if lib_ms is None else {"ms": lib_ms, "tflops": 2.0 * nq * rows * ld_h / (lib_ms / 1e3) / 1e12,
+                                                              "what": "torch.matmul fp16 %d x %d x %d, one launch at a time" % (nq, rows, ld_h)},
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
             "algorithmic": "2*Q*N*D flops per launch, Q=%d N=%d D=%d" % (nq, rows, srch.dim),
             "launch_ms": ms, "peak_source": peaks["source"] + " cuBLAS bf16 burst (fp16 runs on the same kind::f16 pipe)",
