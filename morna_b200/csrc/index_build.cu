@@ -92,10 +92,17 @@ first_position_smem_kernel(const int64_t *__restrict__ row_off, const uint8_t *_
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n_rows; j += warps_total) {
-        if (!pass[j]) continue;
-        const int64_t b = row_off[j], e = row_off[j + 1];
-        for (int64_t p0 = b; p0 < e; p0 += 512) {          // sixteen independent loads in flight per lane
+    int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // the next row's bounds are fetched while the current row streams: one exposed latency per row, not two
+    int64_t b = 0, e = 0;
+    bool ok = false;
+    if (j < n_rows) { ok = pass[j] != 0; b = row_off[j]; e = row_off[j + 1]; }
+    while (j < n_rows) {
+        const int64_t jn = j + warps_total;
+        int64_t bn = 0, en = 0;
+        bool okn = false;
+        if (jn < n_rows) { okn = pass[jn] != 0; bn = row_off[jn]; en = row_off[jn + 1]; }
+        for (int64_t p0 = b; ok && p0 < e; p0 += 512) {     // sixteen independent loads in flight per lane
             int32_t sv[16];
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
@@ -113,6 +120,7 @@ first_position_smem_kernel(const int64_t *__restrict__ row_off, const uint8_t *_
                 }
             }
         }
+        j = jn; b = bn; e = en; ok = okn;
     }
 }
 
