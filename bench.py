@@ -95,6 +95,18 @@ def cpu_baseline_run(n_samples, dim, k, n_queries, threads, seed=1234):
     return n_queries / dt, dt
 
 
+def literal_reference_qps(dim, n_samples, rows=300, seed=1):
+    """The reference as written (pure-Python exact_search_nn, morna.py:681-712, through the literal oracle) on one
+    core: `rows` rows timed, extrapolated linearly to n_samples rows (the loop is one pass over the rows)."""
+    from oracle import morna_oracle as mo
+    rng = np.random.default_rng(seed)
+    S = rng.standard_normal((rows, dim)).astype(np.float32)
+    t0 = time.perf_counter()
+    mo.exact_search_nn(S, S[0].astype(np.float64), 10, clamp=True)
+    dt = time.perf_counter() - t0
+    return 1.0 / (dt * n_samples / rows)
+
+
 def workload_config(n_samples, nq, world, rows_sharded):
     return {"workload": "%d samples x %d features (gaussian, seed 1234), %d in-index queries per GPU per step, "
                         "exact top-%d ids+distances" % (n_samples, DIM, nq, K),
@@ -287,7 +299,10 @@ def main():
             v, dt = cpu_baseline_run(N_SAMPLES, DIM, K, nq_cpu, cores)
             cpu = {"value": v, "unit": "queries/s", "cores": cores, "kind": "port",
                    "sample": "%d of the 4096 queries, C port of exact_search_nn (morna.py:681-712), %d threads, %.1f s"
-                             % (nq_cpu, cores, dt)}
+                             % (nq_cpu, cores, dt),
+                   "reference_as_written_qps": literal_reference_qps(DIM, N_SAMPLES),
+                   "reference_as_written": "the literal pure-Python loop on one core, 300 rows timed and extrapolated to "
+                                           "50000 (the reference itself is Python 2 + annoy + mmh3 and cannot run here)"}
         line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": roofline.pop("dtype"), "data": "synthetic",
