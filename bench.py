@@ -353,10 +353,15 @@ def single_query_line(torch, lib, _lib, device, peaks):
     us = e0.elapsed_time(e1) * 1e3 / reps
     assert torch.equal(out_i, ids) and torch.equal(out_d, d)
     gbs = 4.0 * n * DIM / (us * 1e-6) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "r01_step_summary.json")     # dram bytes per launch from the committed ncu capture
+    if os.path.exists(prof):
+        with open(prof) as fh:
+            traffic = json.load(fh).get("scan64_dram_bytes_21504x3000")
     return {"workload": "21504 samples x 3000 features, one query, exact top-100 (the 258 MB matrix exceeds L2)",
             "us_per_query": us, "queries_per_s": 1e6 / us, "kernel": "scan64_select_kernel<3,2> (one launch per query)",
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                         "algorithmic": "4*N*D bytes per query"}}
+                         "traffic": traffic, "algorithmic": "4*N*D bytes per query"}}
 
 
 def dominant_kernel_roofline(torch, lib, _lib, srch, queries64, peaks):

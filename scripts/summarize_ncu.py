@@ -73,6 +73,13 @@ def full(src, dst_prefix):
     rr = [r for r in out if "rerank_dist" in r["kernel"]]
     if rr:
         summary["rerank_dist_dram_bytes"] = rr[0]["dram_bytes_per_launch"]
+    try:                                   # keys written by other captures (single-query kernel) are kept
+        with open(dst_prefix + ".json") as fh:
+            old = json.load(fh)
+        for k, v in old.items():
+            summary.setdefault(k, v)
+    except Exception:
+        pass
     with open(dst_prefix + ".json", "w") as fh:
         json.dump(summary, fh, indent=1)
     print(open(dst_prefix + ".md").read())
