@@ -7,8 +7,6 @@ frequency, key bytes); ``build`` ships the rows to the device once as binary CSR
 and runs hash -> first-seen ids -> order-faithful scatter-add -> float32 store.
 Annoy's forest (``n_trees``) and the sqlite side files are out of scope.
 """
-import ctypes
-
 import numpy as np
 import torch
 
@@ -117,7 +115,6 @@ class MornaIndex(object):
         if seen_samples is not None and p1 > p0:         # canonical integers: distinct strings == distinct values
             seen_samples.update(np.unique(sample[p0:p1]).astype(str).tolist())
         if self._store_skipped or passing.all():
-            keep = slice(None)
             self._rows.add_block(keys[key_off[r0]:key_off[r1]], np.diff(key_off[r0:r1 + 1]), lens, sample[p0:p1], cov[p0:p1])
             self._pass.extend(passing.astype(np.uint8).tolist())
             self._running_freq.extend(running.tolist())
