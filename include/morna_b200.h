@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MORNA_ABI_VERSION 1
+#define MORNA_ABI_VERSION 2
 
 enum {
     MORNA_OK = 0,
@@ -231,19 +231,32 @@ int morna_knn_batched(const float *vectors, const double *pp, const void *hs, in
                       int32_t *out_ids, double *out_dist, uint8_t *overflow, int32_t *stats,
                       void *workspace, size_t workspace_bytes, void *const *phase_events, void *stream);
 
-/* The two halves of morna_knn_batched, for callers that pipeline consecutive batches on two
- * streams (the scoring half is tensor-core bound, the re-rank half HBM-gather bound, and their
- * kernels are sized to share an SM).  morna_knn_batched_score leaves each query's candidate list
- * in `workspace`; morna_knn_batched_rerank must be given the same workspace, queries, n, nq, k and
- * overflow array and be ordered after it (same stream, or an event). */
+/* The two halves of morna_knn_batched, for callers that pipeline consecutive batches.  The scoring half is
+ * tensor-core bound and leaves LSU, FP64 units and HBM idle; the re-rank half is an HBM/L2 gather.  So the scoring
+ * call of batch i+1 can carry the re-rank of batch i as a SIDE JOB: extra warps inside its GEMM kernels draw the
+ * previous batch's (query, candidate rows) items from a queue in that batch's workspace while the tensor cores run.
+ *
+ *   morna_knn_batched_score(batch i+1, side_job = batch i)    -- same stream
+ *   morna_knn_batched_rerank(batch i, resume = 1)             -- finishes what the helper warps left, orders, writes out
+ *
+ * morna_knn_batched_score leaves each query's candidate list in `workspace`; morna_knn_batched_rerank must be given
+ * the same workspace, queries, n, nq, k and overflow array and be ordered after it (same stream, or an event).
+ * A side job names another batch's arguments exactly as its own morna_knn_batched_rerank call will (its workspace
+ * must differ from the scoring call's).  resume = 0 re-ranks the whole batch (no side job was given). */
+typedef struct morna_rerank_job {
+    const float *vectors; const double *pp; int64_t n; int32_t dim; int64_t ld; int32_t id_base;
+    const double *queries; int64_t nq; int64_t q_ld; int32_t k;
+    const uint8_t *overflow; void *workspace; size_t workspace_bytes;
+} morna_rerank_job;
+
 int morna_knn_batched_score(const void *hs, int64_t ld_h, const float *rho_max, int64_t n, int32_t dim,
                             int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
                             uint8_t *overflow, int32_t *stats, void *workspace, size_t workspace_bytes,
-                            void *const *phase_events, void *stream);
+                            void *const *phase_events, const morna_rerank_job *side_job, void *stream);
 int morna_knn_batched_rerank(const float *vectors, const double *pp, int64_t n, int32_t dim, int64_t ld,
                              int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
                              int32_t *out_ids, double *out_dist, const uint8_t *overflow, void *workspace,
-                             size_t workspace_bytes, void *stream);
+                             size_t workspace_bytes, int32_t resume, void *stream);
 
 /* Test hook: raw fp16 tensor-core scores [nq x n] (n <= 8192) and the per-query bound eps. */
 int morna_debug_tensor_scores(const void *hs, int64_t ld_h, const float *rho_max, int64_t n, int32_t dim,
@@ -254,11 +267,13 @@ int morna_debug_tensor_scores(const void *hs, int64_t ld_h, const float *rho_max
 /* Experiment knobs (process-wide; not part of the drop-in surface; every setting returns the same results):
  *   0  GEMM variant (1 = CTA pairs with cta_group::2, 0 = single CTAs)      1  GEMM pipeline stages (4 or 6)
  *   3  single query: rows per warp pass (1..5, 0 = automatic)               4  index: pipelined barrier-per-row kernel (1) or the simple one (0)
- *   5  re-rank: candidate rows per warp pass (2, 4, 8)                       6  re-rank: MB of rows per L2 phase (0 = no phases)
+ *   5  re-rank: candidate rows per warp pass (2, 4, 8, 16)                   6  re-rank: MB of rows per L2 phase (0 = no phases, -1 = automatic)
  *   7  index: id tiles per bucket column of the barrier-per-row kernel      8  index: 3 = warp-per-range kernel when it pays, 4 = always, 0 = never
  *   9  batched: rows scored between threshold refinements (default 131072)  10 batched: pilot rows (256..8192)
  *   11 batched: rows before the first refinement (0 = key 9's value)        12 index: log2 width of the sample-id ranges (10..12)
- *   13 re-rank: cap on resident CTAs per SM (0 = whatever fits) */
+ *   13 re-rank (CTA-per-query kernel): cap on resident CTAs per SM          14 re-rank kernel: 0 = warp-granular queue items, 1 = CTA per query
+ *   15 re-rank (warp kernel): CTAs per SM (0 = what fits)                   16 re-rank: items per query when not split into phases (0 = 4)
+ *   17 side jobs: 0 = helper warps off (resume calls then re-rank everything) */
 int morna_debug_set_tuning(int32_t key, int32_t value);
 
 #ifdef __cplusplus

@@ -21,6 +21,15 @@ ERR_NO_SAMPLES = -5
 ERR_CAPACITY = -6
 
 _c_i32, _c_i64, _c_sz, _c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t, ctypes.c_void_p
+ABI_VERSION = 2
+
+
+class RerankJob(ctypes.Structure):
+    """morna_rerank_job (include/morna_b200.h): another batch's re-rank, carried by a scoring call."""
+    _fields_ = [("vectors", _c_vp), ("pp", _c_vp), ("n", _c_i64), ("dim", _c_i32), ("ld", _c_i64), ("id_base", _c_i32),
+                ("queries", _c_vp), ("nq", _c_i64), ("q_ld", _c_i64), ("k", _c_i32),
+                ("overflow", _c_vp), ("workspace", _c_vp), ("workspace_bytes", _c_sz)]
+
 
 # name -> (restype, argtypes); mirrors include/morna_b200.h
 _SIGNATURES = {
@@ -60,9 +69,9 @@ _SIGNATURES = {
     "morna_knn_batched": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_i32, _c_i64, _c_i32,
                                          _c_vp, _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_vp, _c_vp]),
     "morna_knn_batched_score": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp, _c_i64, _c_i64, _c_i32,
-                                               _c_vp, _c_vp, _c_vp, _c_sz, _c_vp, _c_vp]),
+                                               _c_vp, _c_vp, _c_vp, _c_sz, _c_vp, ctypes.POINTER(RerankJob), _c_vp]),
     "morna_knn_batched_rerank": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i32, _c_i64, _c_i32, _c_vp, _c_i64, _c_i64, _c_i32,
-                                                _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_vp]),
+                                                _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_i32, _c_vp]),
     "morna_debug_tensor_scores": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_i64, _c_i32, _c_vp, _c_i64, _c_i64, _c_vp,
                                                  _c_i64, _c_vp, _c_vp, _c_sz, _c_vp]),
     "morna_debug_set_tuning": (ctypes.c_int, [_c_i32, _c_i32]),
@@ -91,7 +100,7 @@ def load():
         fn = getattr(lib, name)         # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.morna_abi_version() != 1:
+    if lib.morna_abi_version() != ABI_VERSION:
         raise MornaLibraryError("morna_b200: ABI version mismatch")
     _lib = lib
     return lib

@@ -117,6 +117,343 @@ prep_queries_kernel(const double *__restrict__ queries, int64_t nq, int64_t nq_p
     }
 }
 
+// ------------------------------------------------------------------ exact re-rank + final order
+constexpr int kRrThreads = 128;                // 4 warps per CTA, several CTAs per SM
+constexpr int kOrderThreads = 128;
+
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double2 ldg_f64x2_hint(const double *p, uint64_t pol) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+                 : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
+    return r;
+}
+
+struct RerankParams {
+    const float *vectors; const double *pp; int64_t ld; int32_t dim, id_base, n;
+    const double *queries; int64_t q_ld; const double *qq;
+    const int32_t *fin_id; const int32_t *fin_cnt; const uint8_t *overflow;
+    int32_t fcap, nq, phases, phase_rows;
+    double *fin_dist;
+    unsigned long long *queue;      // warp kernel: next item; zero when the batch's lists are complete
+    int32_t subs;                   // warp kernel: a query's candidate list is dealt out in 32-entry windows to `subs` items
+};
+
+// Exact FP64 distances of every (query, candidate row) pair.  A work item is (query, row phase):
+// the CTA stages the query once in shared memory (pre-multiplied by 2^896, see f32_scaled_f64),
+// compacts the candidates whose rows fall in the phase's row range, and each warp then takes kRows
+// candidate rows at a time so that one shared-memory read of a query chunk feeds kRows FMAs -- the
+// load/store unit, not HBM, limited the one-row-per-warp version.  Per row the sum is the canonical
+// one (lane l owns float4 chunks l, l+32, ...; one accumulator; fixed butterfly), so the distances
+// equal the exact scan's bit for bit.  Items are walked phase-major: with few rows and many queries
+// (rows re-ranked several times per batch) the row range of a phase stays L2-resident while all
+// queries pass over it; phases == 1 is the plain query-major gather.
+template <int kRows>
+__global__ void __launch_bounds__(kRrThreads)
+rerank_dist_kernel(const RerankParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *qs = reinterpret_cast<double *>(smem_raw);                   // [ld]  query * 2^896
+    int *list = reinterpret_cast<int *>(qs + p.ld);                      // [fcap] positions in the candidate list
+    __shared__ int s_count;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chunks = (int)(p.ld >> 2);
+    const uint64_t pol = l2_policy_evict_first();
+    const int64_t total = (int64_t)p.nq * p.phases;
+    for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+        const int ph = (int)(t / p.nq), q = (int)(t - (int64_t)ph * p.nq);
+        if (p.overflow[q]) continue;                                     // answered by the exact scan afterwards
+        const int count = min(p.fin_cnt[q], p.fcap);
+        const int32_t *ids = p.fin_id + (int64_t)q * p.fcap;
+        const int lo = p.id_base + ph * p.phase_rows;
+        const int hi = ph == p.phases - 1 ? INT_MAX : lo + p.phase_rows;
+        __syncthreads();                                                 // previous item is done with qs/list
+        if (warp == 0) {
+            int m = 0;
+            for (int i0 = 0; i0 < count; i0 += 32) {
+                const int i = i0 + lane;
+                const int id = i < count ? ids[i] : -1;
+                const bool keep = i < count && id >= lo && id < hi;
+                const unsigned mask = __ballot_sync(kFull, keep);
+                if (keep) list[m + __popc(mask & ((1u << lane) - 1u))] = i;
+                m += __popc(mask);
+            }
+            if (lane == 0) s_count = m;
+        }
+        __syncthreads();
+        const int m = s_count;
+        if (m == 0) continue;
+        {
+            const double *qsrc = p.queries + (int64_t)q * p.q_ld;
+            if ((p.q_ld & 1) == 0 && (p.dim & 1) == 0) {
+                for (int c = 2 * tid; c < (int)p.ld; c += 2 * kRrThreads) {
+                    double2 v = make_double2(0.0, 0.0);
+                    if (c < p.dim) v = ldg_f64x2_hint(qsrc + c, pol);
+                    qs[c] = v.x * kTwo896; qs[c + 1] = v.y * kTwo896;
+                }
+            } else {
+                for (int c = tid; c < (int)p.ld; c += kRrThreads) qs[c] = c < p.dim ? qsrc[c] * kTwo896 : 0.0;
+            }
+        }
+        __syncthreads();
+        const double qqv = p.qq[q];
+        for (int g = warp * kRows; g < m; g += (kRrThreads / 32) * kRows) {
+            const float4 *src[kRows];
+            int pos[kRows];
+            int64_t row[kRows];
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) {
+                pos[u] = list[min(g + u, m - 1)];                        // the tail repeats the last row
+                row[u] = (int64_t)ids[pos[u]] - p.id_base;
+                src[u] = reinterpret_cast<const float4 *>(p.vectors + row[u] * p.ld);
+            }
+            double acc[kRows];
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) acc[u] = 0.0;
+            int c = lane;
+            for (; c + 32 < chunks; c += 64) {
+                float4 v[2][kRows];
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int u = 0; u < kRows; ++u) v[h][u] = ldg_stream_f4(src[u] + c + 32 * h);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const double2 qa = *reinterpret_cast<const double2 *>(qs + 4 * (c + 32 * h));
+                    const double2 qb = *reinterpret_cast<const double2 *>(qs + 4 * (c + 32 * h) + 2);
+#pragma unroll
+                    for (int u = 0; u < kRows; ++u) {
+                        acc[u] = fma(f32_scaled_f64(v[h][u].x), qa.x, acc[u]);
+                        acc[u] = fma(f32_scaled_f64(v[h][u].y), qa.y, acc[u]);
+                        acc[u] = fma(f32_scaled_f64(v[h][u].z), qb.x, acc[u]);
+                        acc[u] = fma(f32_scaled_f64(v[h][u].w), qb.y, acc[u]);
+                    }
+                }
+            }
+            for (; c < chunks; c += 32) {
+                const double2 qa = *reinterpret_cast<const double2 *>(qs + 4 * c);
+                const double2 qb = *reinterpret_cast<const double2 *>(qs + 4 * c + 2);
+#pragma unroll
+                for (int u = 0; u < kRows; ++u) {
+                    const float4 v = ldg_stream_f4(src[u] + c);
+                    acc[u] = fma(f32_scaled_f64(v.x), qa.x, acc[u]);
+                    acc[u] = fma(f32_scaled_f64(v.y), qa.y, acc[u]);
+                    acc[u] = fma(f32_scaled_f64(v.z), qb.x, acc[u]);
+                    acc[u] = fma(f32_scaled_f64(v.w), qb.y, acc[u]);
+                }
+            }
+            double mine = 0.0;
+            int my_pos = 0;
+            int64_t my_row = 0;
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) {
+                const double s = warp_sum(acc[u]);
+                if (lane == u) { mine = s; my_pos = pos[u]; my_row = row[u]; }
+            }
+            if (lane < kRows && g + lane < m)
+                p.fin_dist[(int64_t)q * p.fcap + my_pos] = angular_from_sums(p.pp[my_row], qqv, mine);
+        }
+    }
+}
+
+// ---- warp-granular re-rank: no shared-memory query, no block barriers -------------------------------------
+// A work item is (row phase, query), taken from a global counter in phase-major order, and belongs to ONE
+// warp: it compacts the query's candidates whose rows lie in the phase's row range (lane-ballot, a 4 KB list
+// per warp), then walks them kRows rows at a time; the query chunk a lane needs is read straight from global
+// memory (L1/L2: the same 24 KB per pass) and pre-multiplied by 2^896, the rows stream past L1.  Because all
+// warps of the GPU draw consecutive items, they work on one phase together: the phase's rows (sized to sit in
+// L2) are fetched from HBM once and then hit in L2 for the other ~Q*k/N queries that list them -- the CTA-per-
+// query kernel above read 3.9 GB from HBM per headline batch for 0.6 GB of distinct rows.  Per row the sum is
+// the canonical one (lane l owns float4 chunks l, l+32, ...; one accumulator; fixed butterfly): bit-equal to
+// the exact scan.  The same device function runs as helper warps inside the GEMM kernel (see knn_gemm2_kernel).
+constexpr int kRwWarps = 8;
+
+__device__ __forceinline__ double2 ldg_f64x2(const double *p) {
+    double2 r;
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+
+// the four query values of chunk c, times 2^896; zero beyond dim
+__device__ __forceinline__ void load_query_chunk(const double *__restrict__ qsrc, int c, int dim, bool vec_ok, double (&qv)[4]) {
+    if (vec_ok && 4 * c + 3 < dim) {
+        const double2 a = ldg_f64x2(qsrc + 4 * c), b = ldg_f64x2(qsrc + 4 * c + 2);
+        qv[0] = a.x * kTwo896; qv[1] = a.y * kTwo896; qv[2] = b.x * kTwo896; qv[3] = b.y * kTwo896;
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) qv[t] = 4 * c + t < dim ? __ldg(qsrc + 4 * c + t) * kTwo896 : 0.0;
+    }
+}
+
+// kRows candidate rows (the first cnt of them live) against one query; kSteps chunk steps of loads in flight
+template <int kRows, int kSteps, bool kAll>
+__device__ __forceinline__ void rerank_rows(const float4 *const (&src)[kRows], int cnt, const double *__restrict__ qsrc,
+                                            int dim, int chunks, bool vec_ok, int lane, double (&acc)[kRows]) {
+#pragma unroll
+    for (int u = 0; u < kRows; ++u) acc[u] = 0.0;
+    int c = lane;
+    for (; c + 32 * (kSteps - 1) < chunks; c += 32 * kSteps) {
+        float4 v[kSteps][kRows];
+#pragma unroll
+        for (int h = 0; h < kSteps; ++h)
+#pragma unroll
+            for (int u = 0; u < kRows; ++u)
+                if (kAll || u < cnt) v[h][u] = ldg_stream_f4(src[u] + c + 32 * h);
+#pragma unroll
+        for (int h = 0; h < kSteps; ++h) {
+            double qv[4];
+            load_query_chunk(qsrc, c + 32 * h, dim, vec_ok, qv);
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) {
+                if (kAll || u < cnt) {
+                    acc[u] = fma(f32_scaled_f64(v[h][u].x), qv[0], acc[u]);
+                    acc[u] = fma(f32_scaled_f64(v[h][u].y), qv[1], acc[u]);
+                    acc[u] = fma(f32_scaled_f64(v[h][u].z), qv[2], acc[u]);
+                    acc[u] = fma(f32_scaled_f64(v[h][u].w), qv[3], acc[u]);
+                }
+            }
+        }
+    }
+    if (kSteps > 1) {
+        for (; c < chunks; c += 32) {
+            double qv[4];
+            load_query_chunk(qsrc, c, dim, vec_ok, qv);
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) {
+                if (kAll || u < cnt) {
+                    const float4 v = ldg_stream_f4(src[u] + c);
+                    acc[u] = fma(f32_scaled_f64(v.x), qv[0], acc[u]);
+                    acc[u] = fma(f32_scaled_f64(v.y), qv[1], acc[u]);
+                    acc[u] = fma(f32_scaled_f64(v.z), qv[2], acc[u]);
+                    acc[u] = fma(f32_scaled_f64(v.w), qv[3], acc[u]);
+                }
+            }
+        }
+    }
+}
+
+template <int kRows, int kSteps>
+__device__ __forceinline__ void rerank_warp_item(const RerankParams &p, long long t, int *list, int lane) {
+    const int sub = (int)(t % p.subs);
+    t /= p.subs;
+    const int ph = (int)(t / p.nq), q = (int)(t - (long long)ph * p.nq);
+    if (p.overflow[q]) return;                                           // answered by the exact scan afterwards
+    const int count = min(p.fin_cnt[q], p.fcap);
+    const int32_t *ids = p.fin_id + (int64_t)q * p.fcap;
+    const int lo = p.id_base + ph * p.phase_rows;
+    const int hi = ph == p.phases - 1 ? INT_MAX : lo + p.phase_rows;
+    int m = 0;
+    for (int i0 = 32 * sub; i0 < count; i0 += 32 * p.subs) {
+        const int i = i0 + lane;
+        const int id = i < count ? ids[i] : -1;
+        const bool keep = i < count && id >= lo && id < hi;
+        const unsigned mask = __ballot_sync(kFull, keep);
+        if (keep) list[m + __popc(mask & ((1u << lane) - 1u))] = i;
+        m += __popc(mask);
+    }
+    if (m == 0) return;
+    __syncwarp();
+    const double *qsrc = p.queries + (int64_t)q * p.q_ld;
+    const bool vec_ok = ((p.q_ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.queries) & 15) == 0);
+    const int chunks = (int)(p.ld >> 2);
+    const double qqv = p.qq[q];
+    for (int g = 0; g < m; g += kRows) {
+        const int cnt = min(kRows, m - g);
+        const float4 *src[kRows];
+        int my_pos = 0;
+        int64_t my_row = 0;
+#pragma unroll
+        for (int u = 0; u < kRows; ++u) {
+            const int pos = list[min(g + u, m - 1)];
+            const int64_t row = (int64_t)ids[pos] - p.id_base;
+            src[u] = reinterpret_cast<const float4 *>(p.vectors + row * p.ld);
+            if (lane == u) { my_pos = pos; my_row = row; }
+        }
+        double acc[kRows];
+        rerank_rows<kRows, kSteps, false>(src, cnt, qsrc, p.dim, chunks, vec_ok, lane, acc);
+        double mine = 0.0;
+#pragma unroll
+        for (int u = 0; u < kRows; ++u) {
+            if (u < cnt) {                                               // cnt is warp-uniform
+                const double s = warp_sum(acc[u]);
+                if (lane == u) mine = s;
+            }
+        }
+        if (lane < cnt) p.fin_dist[(int64_t)q * p.fcap + my_pos] = angular_from_sums(p.pp[my_row], qqv, mine);
+    }
+    __syncwarp();
+}
+
+// draws items until the counter passes the end (or *stop turns non-zero, for helper warps that must leave with their CTA)
+template <int kRows, int kSteps>
+__device__ __forceinline__ void rerank_warp_loop(const RerankParams &p, int *list, int lane, const volatile int *stop) {
+    const long long total = (long long)p.nq * p.phases * p.subs;
+    for (;;) {
+        if (stop && *stop) break;
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(p.queue, 1ull);
+        t = __shfl_sync(kFull, t, 0);
+        if ((long long)t >= total) break;
+        rerank_warp_item<kRows, kSteps>(p, (long long)t, list, lane);
+    }
+}
+
+template <int kRows, int kSteps>
+__global__ void __launch_bounds__(kRwWarps * 32, 2)
+rerank_warp_kernel(const RerankParams p) {
+    extern __shared__ __align__(16) int rw_lists[];                      // [kRwWarps][fcap]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    rerank_warp_loop<kRows, kSteps>(p, rw_lists + warp * p.fcap, lane, nullptr);
+}
+
+// One CTA per query: candidates sorted under the reference order (bitonic network in shared
+// memory), first k written out; short lists are padded with id -1 / +inf.
+__global__ void __launch_bounds__(kOrderThreads)
+rerank_order_kernel(const int32_t *__restrict__ fin_id, const int32_t *__restrict__ fin_cnt,
+                    const double *__restrict__ fin_dist, const uint8_t *__restrict__ overflow, int32_t fcap,
+                    int32_t k, int32_t *__restrict__ out_ids, double *__restrict__ out_dist) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sd = reinterpret_cast<double *>(smem_raw);                 // [P]
+    int *si = reinterpret_cast<int *>(sd + fcap);                      // [P]
+    const int tid = threadIdx.x, q = blockIdx.x;
+    int32_t *oi = out_ids + (int64_t)q * k;
+    double *od = out_dist + (int64_t)q * k;
+    if (overflow[q]) {
+        for (int i = tid; i < k; i += kOrderThreads) { oi[i] = -1; od[i] = INFINITY; }
+        return;
+    }
+    const int count = min(fin_cnt[q], fcap);
+    int P = 32;
+    while (P < count) P <<= 1;
+    for (int i = tid; i < P; i += kOrderThreads) {
+        const bool have = i < count;
+        sd[i] = have ? fin_dist[(int64_t)q * fcap + i] : INFINITY;
+        si[i] = have ? fin_id[(int64_t)q * fcap + i] : -1;
+    }
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = tid; i < (P >> 1); i += kOrderThreads) {
+                int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                bool asc = (lo & size) == 0;
+                double dl = sd[lo], dh = sd[hi];
+                int il = si[lo], ih = si[hi];
+                bool swap = asc ? before(dh, ih, dl, il) : before(dl, il, dh, ih);
+                if (swap) { sd[lo] = dh; sd[hi] = dl; si[lo] = ih; si[hi] = il; }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < k; i += kOrderThreads) {
+        bool ok = i < count && si[i] >= 0;
+        oi[i] = ok ? si[i] : -1;
+        od[i] = ok ? sd[i] : INFINITY;
+    }
+}
+
 // ------------------------------------------------------------------ GEMM + filter epilogue
 namespace gemm {
 constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
@@ -278,9 +615,12 @@ knn_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 namespace gemm2 {
 constexpr int BM = 128, BN = 256, BN_HALF = 128, BK = 64, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN_HALF * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
-constexpr int THREADS = 192;
+constexpr int THREADS = 192;                   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int HELPER_WARPS = 8;                // warps 6-13: re-rank items of the PREVIOUS batch (LSU/FP64/HBM are idle under the MMAs)
+constexpr int THREADS_ALL = THREADS + 32 * HELPER_WARPS;
 constexpr int ACC_STAGES = 2, TMEM_COLS = ACC_STAGES * BN;
-constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 + 256; }
+constexpr int HELPER_BYTES = HELPER_WARPS * 1024 * 4 + 16;          // a candidate list per helper warp + the stop flag
+constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 + 256 + HELPER_BYTES; }
 }  // namespace gemm2
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -297,9 +637,14 @@ __device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {
     return r;
 }
 
+// Warps 6-13 take no part in the GEMM: while the tensor cores work through this batch's tiles they draw re-rank
+// items of the previous batch (rr.queue != nullptr) from its queue -- the re-rank is a gather of candidate rows
+// through LSU + FP64 units the GEMM leaves idle.  They stop taking items when this CTA's epilogue has finished
+// its last tile; whatever is left in the queue is drained by rerank_warp_kernel afterwards.
 template <int kStages>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm2::THREADS, 1)
-knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_s, GemmParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm2::THREADS_ALL, 1)
+knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_s, GemmParams p,
+                 const RerankParams rr) {
     using namespace gemm2;
     using namespace tc;
     extern __shared__ uint8_t smem_raw[];
@@ -312,6 +657,8 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t tmem_slot = bars + 8u * (2 * kStages + 2 * ACC_STAGES);
     volatile uint32_t *tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    int *helper_lists = reinterpret_cast<int *>(smem_raw + (bars + 256u - smem_u32(smem_raw)));     // [HELPER_WARPS][1024]
+    volatile int *helper_stop = helper_lists + HELPER_WARPS * 1024;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -324,6 +671,7 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
         fence_barrier_init();
+        *helper_stop = 0;
     }
     if (warp == 2) {
         tmem_alloc<2>(tmem_slot, TMEM_COLS);
@@ -378,6 +726,8 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
         }
+    } else if (warp >= THREADS / 32) {     // ===== helper warps: re-rank items of the previous batch
+        if (rr.queue) rerank_warp_loop<8, 2>(rr, helper_lists + (warp - THREADS / 32) * 1024, lane, helper_stop);
     } else {                 // ===== epilogue: thread = TMEM lane = query row of this CTA's half
         const int quarter = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
@@ -436,6 +786,7 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             mbar_arrive_cluster(tempty_bar(acc), 0);       // the leader's MMA thread waits for both CTAs
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
+        if (warp == 2 && lane == 0) *helper_stop = 1;      // this CTA's tiles are done: helpers finish their item and leave
     }
     tc_fence_before();
     cluster_sync_all();
@@ -631,191 +982,6 @@ kth_warp_kernel(KthParams p, int nq) {
     }
 }
 
-// ------------------------------------------------------------------ exact re-rank + final order
-constexpr int kRrThreads = 128;                // 4 warps per CTA, several CTAs per SM
-constexpr int kOrderThreads = 128;
-
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ double2 ldg_f64x2_hint(const double *p, uint64_t pol) {
-    double2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
-                 : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
-    return r;
-}
-
-struct RerankParams {
-    const float *vectors; const double *pp; int64_t ld; int32_t dim, id_base, n;
-    const double *queries; int64_t q_ld; const double *qq;
-    const int32_t *fin_id; const int32_t *fin_cnt; const uint8_t *overflow;
-    int32_t fcap, nq, phases, phase_rows;
-    double *fin_dist;
-};
-
-// Exact FP64 distances of every (query, candidate row) pair.  A work item is (query, row phase):
-// the CTA stages the query once in shared memory (pre-multiplied by 2^896, see f32_scaled_f64),
-// compacts the candidates whose rows fall in the phase's row range, and each warp then takes kRows
-// candidate rows at a time so that one shared-memory read of a query chunk feeds kRows FMAs -- the
-// load/store unit, not HBM, limited the one-row-per-warp version.  Per row the sum is the canonical
-// one (lane l owns float4 chunks l, l+32, ...; one accumulator; fixed butterfly), so the distances
-// equal the exact scan's bit for bit.  Items are walked phase-major: with few rows and many queries
-// (rows re-ranked several times per batch) the row range of a phase stays L2-resident while all
-// queries pass over it; phases == 1 is the plain query-major gather.
-template <int kRows>
-__global__ void __launch_bounds__(kRrThreads)
-rerank_dist_kernel(const RerankParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *qs = reinterpret_cast<double *>(smem_raw);                   // [ld]  query * 2^896
-    int *list = reinterpret_cast<int *>(qs + p.ld);                      // [fcap] positions in the candidate list
-    __shared__ int s_count;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int chunks = (int)(p.ld >> 2);
-    const uint64_t pol = l2_policy_evict_first();
-    const int64_t total = (int64_t)p.nq * p.phases;
-    for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
-        const int ph = (int)(t / p.nq), q = (int)(t - (int64_t)ph * p.nq);
-        if (p.overflow[q]) continue;                                     // answered by the exact scan afterwards
-        const int count = min(p.fin_cnt[q], p.fcap);
-        const int32_t *ids = p.fin_id + (int64_t)q * p.fcap;
-        const int lo = p.id_base + ph * p.phase_rows;
-        const int hi = ph == p.phases - 1 ? INT_MAX : lo + p.phase_rows;
-        __syncthreads();                                                 // previous item is done with qs/list
-        if (warp == 0) {
-            int m = 0;
-            for (int i0 = 0; i0 < count; i0 += 32) {
-                const int i = i0 + lane;
-                const int id = i < count ? ids[i] : -1;
-                const bool keep = i < count && id >= lo && id < hi;
-                const unsigned mask = __ballot_sync(kFull, keep);
-                if (keep) list[m + __popc(mask & ((1u << lane) - 1u))] = i;
-                m += __popc(mask);
-            }
-            if (lane == 0) s_count = m;
-        }
-        __syncthreads();
-        const int m = s_count;
-        if (m == 0) continue;
-        {
-            const double *qsrc = p.queries + (int64_t)q * p.q_ld;
-            if ((p.q_ld & 1) == 0 && (p.dim & 1) == 0) {
-                for (int c = 2 * tid; c < (int)p.ld; c += 2 * kRrThreads) {
-                    double2 v = make_double2(0.0, 0.0);
-                    if (c < p.dim) v = ldg_f64x2_hint(qsrc + c, pol);
-                    qs[c] = v.x * kTwo896; qs[c + 1] = v.y * kTwo896;
-                }
-            } else {
-                for (int c = tid; c < (int)p.ld; c += kRrThreads) qs[c] = c < p.dim ? qsrc[c] * kTwo896 : 0.0;
-            }
-        }
-        __syncthreads();
-        const double qqv = p.qq[q];
-        for (int g = warp * kRows; g < m; g += (kRrThreads / 32) * kRows) {
-            const float4 *src[kRows];
-            int pos[kRows];
-            int64_t row[kRows];
-#pragma unroll
-            for (int u = 0; u < kRows; ++u) {
-                pos[u] = list[min(g + u, m - 1)];                        // the tail repeats the last row
-                row[u] = (int64_t)ids[pos[u]] - p.id_base;
-                src[u] = reinterpret_cast<const float4 *>(p.vectors + row[u] * p.ld);
-            }
-            double acc[kRows];
-#pragma unroll
-            for (int u = 0; u < kRows; ++u) acc[u] = 0.0;
-            int c = lane;
-            for (; c + 32 < chunks; c += 64) {
-                float4 v[2][kRows];
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int u = 0; u < kRows; ++u) v[h][u] = ldg_stream_f4(src[u] + c + 32 * h);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const double2 qa = *reinterpret_cast<const double2 *>(qs + 4 * (c + 32 * h));
-                    const double2 qb = *reinterpret_cast<const double2 *>(qs + 4 * (c + 32 * h) + 2);
-#pragma unroll
-                    for (int u = 0; u < kRows; ++u) {
-                        acc[u] = fma(f32_scaled_f64(v[h][u].x), qa.x, acc[u]);
-                        acc[u] = fma(f32_scaled_f64(v[h][u].y), qa.y, acc[u]);
-                        acc[u] = fma(f32_scaled_f64(v[h][u].z), qb.x, acc[u]);
-                        acc[u] = fma(f32_scaled_f64(v[h][u].w), qb.y, acc[u]);
-                    }
-                }
-            }
-            for (; c < chunks; c += 32) {
-                const double2 qa = *reinterpret_cast<const double2 *>(qs + 4 * c);
-                const double2 qb = *reinterpret_cast<const double2 *>(qs + 4 * c + 2);
-#pragma unroll
-                for (int u = 0; u < kRows; ++u) {
-                    const float4 v = ldg_stream_f4(src[u] + c);
-                    acc[u] = fma(f32_scaled_f64(v.x), qa.x, acc[u]);
-                    acc[u] = fma(f32_scaled_f64(v.y), qa.y, acc[u]);
-                    acc[u] = fma(f32_scaled_f64(v.z), qb.x, acc[u]);
-                    acc[u] = fma(f32_scaled_f64(v.w), qb.y, acc[u]);
-                }
-            }
-            double mine = 0.0;
-            int my_pos = 0;
-            int64_t my_row = 0;
-#pragma unroll
-            for (int u = 0; u < kRows; ++u) {
-                const double s = warp_sum(acc[u]);
-                if (lane == u) { mine = s; my_pos = pos[u]; my_row = row[u]; }
-            }
-            if (lane < kRows && g + lane < m)
-                p.fin_dist[(int64_t)q * p.fcap + my_pos] = angular_from_sums(p.pp[my_row], qqv, mine);
-        }
-    }
-}
-
-// One CTA per query: candidates sorted under the reference order (bitonic network in shared
-// memory), first k written out; short lists are padded with id -1 / +inf.
-__global__ void __launch_bounds__(kOrderThreads)
-rerank_order_kernel(const int32_t *__restrict__ fin_id, const int32_t *__restrict__ fin_cnt,
-                    const double *__restrict__ fin_dist, const uint8_t *__restrict__ overflow, int32_t fcap,
-                    int32_t k, int32_t *__restrict__ out_ids, double *__restrict__ out_dist) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *sd = reinterpret_cast<double *>(smem_raw);                 // [P]
-    int *si = reinterpret_cast<int *>(sd + fcap);                      // [P]
-    const int tid = threadIdx.x, q = blockIdx.x;
-    int32_t *oi = out_ids + (int64_t)q * k;
-    double *od = out_dist + (int64_t)q * k;
-    if (overflow[q]) {
-        for (int i = tid; i < k; i += kOrderThreads) { oi[i] = -1; od[i] = INFINITY; }
-        return;
-    }
-    const int count = min(fin_cnt[q], fcap);
-    int P = 32;
-    while (P < count) P <<= 1;
-    for (int i = tid; i < P; i += kOrderThreads) {
-        const bool have = i < count;
-        sd[i] = have ? fin_dist[(int64_t)q * fcap + i] : INFINITY;
-        si[i] = have ? fin_id[(int64_t)q * fcap + i] : -1;
-    }
-    for (int size = 2; size <= P; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            __syncthreads();
-            for (int i = tid; i < (P >> 1); i += kOrderThreads) {
-                int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
-                bool asc = (lo & size) == 0;
-                double dl = sd[lo], dh = sd[hi];
-                int il = si[lo], ih = si[hi];
-                bool swap = asc ? before(dh, ih, dl, il) : before(dl, il, dh, ih);
-                if (swap) { sd[lo] = dh; sd[hi] = dl; si[lo] = ih; si[hi] = il; }
-            }
-        }
-    }
-    __syncthreads();
-    for (int i = tid; i < k; i += kOrderThreads) {
-        bool ok = i < count && si[i] >= 0;
-        oi[i] = ok ? si[i] : -1;
-        od[i] = ok ? sd[i] : INFINITY;
-    }
-}
-
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -870,10 +1036,15 @@ static int g_pilot_rows = kKthMax; // rows of the pilot block whose scores are d
 static int g_first_block = 0;      // rows up to the first refinement (key 11); 0 = g_block_rows
 static int g_rerank_ctas_per_sm = 0; // key 13: cap on resident re-rank CTAs per SM (0 = whatever fits)
 static int g_rerank_rows = 8;     // candidate rows per warp pass of the re-rank (2, 4 or 8)
-static int g_rerank_phase_mb = 0;  // row range kept L2-resident per re-rank phase; 0 = never split into phases
+static int g_rerank_phase_mb = -1; // row range kept L2-resident per re-rank phase; 0 = never split; -1 = 64 MB for the warp kernel, unsplit otherwise
+static int g_rerank_kernel = 0;    // key 14: 0 = warp-granular items from a global queue, 1 = one CTA per query (shared-memory query)
+static int g_rerank_ctas = 0;      // key 15: CTAs per SM of the warp kernel (0 = what fits)
+static int g_rerank_subs = 0;      // key 16: items per query of the unsplit warp re-rank (0 = 4)
+static int g_side_job = 1;         // key 17: 0 = ignore side jobs (the resume call then re-ranks everything)
 
 
-static int launch_knn_gemm(const CUtensorMap &tmap_q, const CUtensorMap &tmap_s, const GemmParams &gp, cudaStream_t s) {
+static int launch_knn_gemm(const CUtensorMap &tmap_q, const CUtensorMap &tmap_s, const GemmParams &gp, cudaStream_t s,
+                           const RerankParams *side = nullptr) {
     if (!g_gemm_pair) {
         static bool attr_set = false;
         if (!attr_set) {
@@ -894,13 +1065,15 @@ static int launch_knn_gemm(const CUtensorMap &tmap_q, const CUtensorMap &tmap_s,
     int tiles = ((gp.m_blocks + 1) / 2) * gp.n_tiles;
     int pairs = sm_count_b() / 2;
     if (tiles < pairs) pairs = tiles;
-    kern<<<2 * pairs, gemm2::THREADS, smem, s>>>(tmap_q, tmap_s, gp);
+    RerankParams rr{};
+    if (side) rr = *side;
+    kern<<<2 * pairs, gemm2::THREADS_ALL, smem, s>>>(tmap_q, tmap_s, gp, rr);
     MORNA_LAUNCH_CHECK();
     return MORNA_OK;
 }
 
 struct BatchWs {
-    size_t hq, qq, eps, pilot, thr, cand_score, cand_id, cand2_score, cand2_id, cand_cnt, fin_id, fin_cnt, fin_dist, total;
+    size_t hq, qq, eps, pilot, thr, cand_score, cand_id, cand2_score, cand2_id, cand_cnt, fin_id, fin_cnt, fin_dist, queue, total;
     int64_t nq_pad, n0, pilot_ld;
 };
 static BatchWs batch_ws_layout(int64_t n, int64_t nq, int64_t ld_h) {
@@ -926,9 +1099,14 @@ static BatchWs batch_ws_layout(int64_t n, int64_t nq, int64_t ld_h) {
     w.fin_id = take((size_t)nq * kFinCap * sizeof(int32_t));
     w.fin_cnt = take((size_t)nq * sizeof(int32_t));
     w.fin_dist = take((size_t)nq * kFinCap * sizeof(double));
+    w.queue = take(sizeof(unsigned long long));
     w.total = off + 1024;
     return w;
 }
+
+static int make_rerank_params(RerankParams &rp, bool &warp_kernel, const float *vectors, const double *pp, int64_t n,
+                              int32_t dim, int64_t ld, int32_t id_base, const double *queries, int64_t nq, int64_t q_ld,
+                              int32_t k, const uint8_t *overflow, void *workspace, size_t workspace_bytes);
 
 }  // namespace morna
 
@@ -962,12 +1140,23 @@ extern "C" size_t morna_knn_batched_workspace_bytes(int64_t n, int64_t nq, int32
 extern "C" int morna_knn_batched_score(const void *hs, int64_t ld_h, const float *rho_max, int64_t n, int32_t dim,
                                        int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
                                        uint8_t *overflow, int32_t *stats, void *workspace, size_t workspace_bytes,
-                                       void *const *phase_events, void *stream) {
+                                       void *const *phase_events, const morna_rerank_job *side_job, void *stream) {
     if (!hs || !rho_max || !queries || !overflow || !stats || n <= 0 || n > kBatchedMaxRows || nq <= 0 || dim <= 0 ||
         q_ld < dim || k <= 0 || k > kFinCap / 2 || ld_h != morna_tensor_operand_ld(dim))
         return MORNA_ERR_INVALID_ARGUMENT;
     BatchWs w = batch_ws_layout(n, nq, ld_h);
     if (!workspace || workspace_bytes < w.total) return MORNA_ERR_WORKSPACE_TOO_SMALL;
+    RerankParams side{};
+    const RerankParams *side_ptr = nullptr;
+    if (side_job) {                 // the previous batch's re-rank rides in this batch's GEMM launches
+        if (side_job->workspace == workspace) return MORNA_ERR_INVALID_ARGUMENT;
+        bool warp_kernel = true;
+        int rcj = make_rerank_params(side, warp_kernel, side_job->vectors, side_job->pp, side_job->n, side_job->dim,
+                                     side_job->ld, side_job->id_base, side_job->queries, side_job->nq, side_job->q_ld,
+                                     side_job->k, side_job->overflow, side_job->workspace, side_job->workspace_bytes);
+        if (rcj != MORNA_OK) return rcj;
+        if (warp_kernel && g_gemm_pair && g_side_job) side_ptr = &side;      // otherwise everything is left to the resume call
+    }
     cudaStream_t s = (cudaStream_t)stream;
     unsigned char *ws = (unsigned char *)workspace;
     __half *hq = (__half *)(ws + w.hq);
@@ -987,6 +1176,7 @@ extern "C" int morna_knn_batched_score(const void *hs, int64_t ld_h, const float
     MORNA_CUDA_TRY(cudaMemsetAsync(overflow, 0, (size_t)nq, s));
     MORNA_CUDA_TRY(cudaMemsetAsync(stats, 0, 4 * sizeof(int32_t), s));
     MORNA_CUDA_TRY(cudaMemsetAsync(cand_cnt, 0, (size_t)nq * sizeof(int32_t), s));
+    MORNA_CUDA_TRY(cudaMemsetAsync(ws + w.queue, 0, sizeof(unsigned long long), s));     // this batch's re-rank queue
 
     // fp32 accumulation of dim products, each add off by at most one truncation ulp of a
     // partial sum bounded by |h_s||h_q| <= ~1; chain length dim/16 MMAs plus the in-MMA tree
@@ -1011,7 +1201,7 @@ extern "C" int morna_knn_batched_score(const void *hs, int64_t ld_h, const float
     auto launch_gemm = [&](int32_t n_begin, int32_t n_end, int32_t mode) -> int {
         gp.n_begin = n_begin; gp.n_end = n_end; gp.mode = mode;
         gp.n_tiles = (n_end - n_begin + gemm::BN - 1) / gemm::BN;
-        return launch_knn_gemm(tmap_q, tmap_s, gp, s);
+        return launch_knn_gemm(tmap_q, tmap_s, gp, s, side_ptr);
     };
     KthParams kp{};
     kp.k = k; kp.n0 = (int32_t)w.n0; kp.n_begin = 0; kp.id_base = id_base; kp.cap = kCandCap; kp.fcap = kFinCap;
@@ -1057,53 +1247,94 @@ extern "C" int morna_knn_batched_score(const void *hs, int64_t ld_h, const float
     return MORNA_OK;
 }
 
-// Re-rank half: exact FP64 distances of the candidate lists a previous morna_knn_batched_score left
-// in the same workspace, ordered under the reference rule (HBM-gather bound; no tensor cores).
-extern "C" int morna_knn_batched_rerank(const float *vectors, const double *pp, int64_t n, int32_t dim, int64_t ld,
-                                        int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
-                                        int32_t *out_ids, double *out_dist, const uint8_t *overflow, void *workspace,
-                                        size_t workspace_bytes, void *stream) {
-    if (!vectors || !pp || !queries || !out_ids || !out_dist || !overflow || n <= 0 || n > kBatchedMaxRows ||
-        nq <= 0 || dim <= 0 || ld < dim || (ld & 3) || q_ld < dim || k <= 0 || k > kFinCap / 2)
+namespace morna {
+
+// parameters of a batch's re-rank from the workspace its scoring half filled
+static int make_rerank_params(RerankParams &rp, bool &warp_kernel, const float *vectors, const double *pp, int64_t n,
+                              int32_t dim, int64_t ld, int32_t id_base, const double *queries, int64_t nq, int64_t q_ld,
+                              int32_t k, const uint8_t *overflow, void *workspace, size_t workspace_bytes) {
+    if (!vectors || !pp || !queries || !overflow || n <= 0 || n > kBatchedMaxRows || nq <= 0 || dim <= 0 || ld < dim ||
+        (ld & 3) || q_ld < dim || k <= 0 || k > kFinCap / 2)
         return MORNA_ERR_INVALID_ARGUMENT;
     BatchWs w = batch_ws_layout(n, nq, morna_tensor_operand_ld(dim));
     if (!workspace || workspace_bytes < w.total) return MORNA_ERR_WORKSPACE_TOO_SMALL;
-    cudaStream_t s = (cudaStream_t)stream;
     unsigned char *ws = (unsigned char *)workspace;
-    const double *qq = (const double *)(ws + w.qq);
-    const int32_t *fin_id = (const int32_t *)(ws + w.fin_id);
-    const int32_t *fin_cnt = (const int32_t *)(ws + w.fin_cnt);
-    RerankParams rp{};
+    rp = RerankParams{};
     rp.vectors = vectors; rp.pp = pp; rp.ld = ld; rp.dim = dim; rp.id_base = id_base; rp.n = (int32_t)n;
-    rp.queries = queries; rp.q_ld = q_ld; rp.qq = qq; rp.fin_id = fin_id; rp.fin_cnt = fin_cnt; rp.overflow = overflow;
+    rp.queries = queries; rp.q_ld = q_ld; rp.qq = (const double *)(ws + w.qq);
+    rp.fin_id = (const int32_t *)(ws + w.fin_id); rp.fin_cnt = (const int32_t *)(ws + w.fin_cnt); rp.overflow = overflow;
     rp.fcap = kFinCap; rp.nq = (int32_t)nq; rp.fin_dist = (double *)(ws + w.fin_dist);
+    rp.queue = (unsigned long long *)(ws + w.queue);
     // phases: only when a row is re-ranked several times per batch (otherwise every row is read at
-    // most about once and splitting would only re-stage the queries)
-    rp.phases = 1; rp.phase_rows = (int32_t)n;
+    // most about once and splitting would only re-read the queries)
+    rp.phases = 1; rp.phase_rows = (int32_t)n; rp.subs = 1;
     const double reuse = (double)nq * (1.2 * k) / (double)n;
-    if (g_rerank_phase_mb > 0 && reuse >= 3.0) {
-        int64_t rows = ((int64_t)g_rerank_phase_mb << 20) / ((int64_t)ld * 4);
+    const size_t rr_smem = (size_t)ld * sizeof(double) + (size_t)kFinCap * sizeof(int);
+    warp_kernel = g_rerank_kernel == 0 || rr_smem > 200 * 1024;
+    const int phase_mb = g_rerank_phase_mb >= 0 ? g_rerank_phase_mb : (warp_kernel ? 64 : 0);
+    if (phase_mb > 0 && reuse >= 3.0) {
+        int64_t rows = ((int64_t)phase_mb << 20) / ((int64_t)ld * 4);
         if (rows < 1024) rows = 1024;
         if (rows < n) {
             rp.phases = (int32_t)((n + rows - 1) / rows);
             rp.phase_rows = (int32_t)((n + rp.phases - 1) / rp.phases);
         }
     }
-    const size_t rr_smem = (size_t)ld * sizeof(double) + (size_t)kFinCap * sizeof(int);
-    if (rr_smem > 200 * 1024) return MORNA_ERR_INVALID_ARGUMENT;
-    auto kern = g_rerank_rows == 8 ? rerank_dist_kernel<8> : g_rerank_rows == 2 ? rerank_dist_kernel<2> : rerank_dist_kernel<4>;
-    MORNA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
-    int per_sm = 0;
-    MORNA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRrThreads, rr_smem));
-    if (per_sm < 1) per_sm = 1;
-    if (g_rerank_ctas_per_sm > 0 && per_sm > g_rerank_ctas_per_sm) per_sm = g_rerank_ctas_per_sm;
-    const int64_t items = (int64_t)nq * rp.phases;
-    int64_t rr_grid = (int64_t)per_sm * sm_count_b();
-    if (rr_grid > items) rr_grid = items;
-    kern<<<(unsigned)rr_grid, kRrThreads, rr_smem, s>>>(rp);
-    MORNA_LAUNCH_CHECK();
+    if (warp_kernel && rp.phases == 1) rp.subs = g_rerank_subs > 0 ? g_rerank_subs : 4;     // short items: helper warps leave promptly
+    return MORNA_OK;
+}
+
+}  // namespace morna
+
+// Re-rank half: exact FP64 distances of the candidate lists a previous morna_knn_batched_score left
+// in the same workspace, ordered under the reference rule (HBM/L2-gather bound; no tensor cores).
+// resume != 0: a later morna_knn_batched_score call carried this batch as its side job -- only what its
+// helper warps left in the queue is re-ranked here.
+extern "C" int morna_knn_batched_rerank(const float *vectors, const double *pp, int64_t n, int32_t dim, int64_t ld,
+                                        int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
+                                        int32_t *out_ids, double *out_dist, const uint8_t *overflow, void *workspace,
+                                        size_t workspace_bytes, int32_t resume, void *stream) {
+    if (!out_ids || !out_dist) return MORNA_ERR_INVALID_ARGUMENT;
+    RerankParams rp;
+    bool warp_kernel = true;
+    int rc = make_rerank_params(rp, warp_kernel, vectors, pp, n, dim, ld, id_base, queries, nq, q_ld, k, overflow, workspace,
+                                workspace_bytes);
+    if (rc != MORNA_OK) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (warp_kernel) {
+        // warp-granular items (any dim: the query is read from global memory)
+        if (!resume) MORNA_CUDA_TRY(cudaMemsetAsync(rp.queue, 0, sizeof(unsigned long long), s));
+        auto kern = g_rerank_rows == 16 ? rerank_warp_kernel<16, 1> : g_rerank_rows == 4 ? rerank_warp_kernel<4, 4>
+                                                                                       : rerank_warp_kernel<8, 2>;
+        const size_t smem = (size_t)kRwWarps * kFinCap * sizeof(int);
+        // shared-memory carve-out at its maximum, so that CTAs of this kernel and the GEMM (130 KB) can share an SM
+        MORNA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int per_sm = 0;
+        MORNA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRwWarps * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        if (g_rerank_ctas > 0 && per_sm > g_rerank_ctas) per_sm = g_rerank_ctas;
+        const int64_t items = (int64_t)nq * rp.phases * rp.subs;
+        int64_t grid = (int64_t)per_sm * sm_count_b();
+        if (grid * kRwWarps > items) grid = (items + kRwWarps - 1) / kRwWarps;
+        kern<<<(unsigned)grid, kRwWarps * 32, smem, s>>>(rp);
+        MORNA_LAUNCH_CHECK();
+    } else {
+        if (resume) return MORNA_ERR_INVALID_ARGUMENT;
+        const size_t rr_smem = (size_t)ld * sizeof(double) + (size_t)kFinCap * sizeof(int);
+        auto kern = g_rerank_rows == 2 ? rerank_dist_kernel<2> : g_rerank_rows == 4 ? rerank_dist_kernel<4> : rerank_dist_kernel<8>;
+        MORNA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
+        int per_sm = 0;
+        MORNA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRrThreads, rr_smem));
+        if (per_sm < 1) per_sm = 1;
+        if (g_rerank_ctas_per_sm > 0 && per_sm > g_rerank_ctas_per_sm) per_sm = g_rerank_ctas_per_sm;
+        const int64_t items = (int64_t)nq * rp.phases;
+        int64_t rr_grid = (int64_t)per_sm * sm_count_b();
+        if (rr_grid > items) rr_grid = items;
+        kern<<<(unsigned)rr_grid, kRrThreads, rr_smem, s>>>(rp);
+        MORNA_LAUNCH_CHECK();
+    }
     const size_t or_smem = (size_t)kFinCap * (sizeof(double) + sizeof(int));
-    rerank_order_kernel<<<(unsigned)nq, kOrderThreads, or_smem, s>>>(fin_id, fin_cnt, rp.fin_dist, overflow, kFinCap, k,
+    rerank_order_kernel<<<(unsigned)nq, kOrderThreads, or_smem, s>>>(rp.fin_id, rp.fin_cnt, rp.fin_dist, overflow, kFinCap, k,
                                                                     out_ids, out_dist);
     MORNA_LAUNCH_CHECK();
     return MORNA_OK;
@@ -1116,10 +1347,10 @@ extern "C" int morna_knn_batched(const float *vectors, const double *pp, const v
                                  size_t workspace_bytes, void *const *phase_events, void *stream) {
     if (!vectors || !pp || !out_ids || !out_dist || ld < dim || (ld & 3)) return MORNA_ERR_INVALID_ARGUMENT;
     int rc = morna_knn_batched_score(hs, ld_h, rho_max, n, dim, id_base, queries, nq, q_ld, k, overflow, stats,
-                                     workspace, workspace_bytes, phase_events, stream);
+                                     workspace, workspace_bytes, phase_events, nullptr, stream);
     if (rc != MORNA_OK) return rc;
     rc = morna_knn_batched_rerank(vectors, pp, n, dim, ld, id_base, queries, nq, q_ld, k, out_ids, out_dist, overflow,
-                                  workspace, workspace_bytes, stream);
+                                  workspace, workspace_bytes, 0, stream);
     if (rc == MORNA_OK && phase_events) cudaEventRecord((cudaEvent_t)phase_events[6], (cudaStream_t)stream);
     return rc;
 }
@@ -1174,6 +1405,10 @@ extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
     else if (key == 8) morna::set_acc_variant(value);
     else if (key == 12) morna::set_acc_shift(value);
     else if (key == 6) g_rerank_phase_mb = value;
+    else if (key == 14) g_rerank_kernel = value;
+    else if (key == 15) g_rerank_ctas = value;
+    else if (key == 16) g_rerank_subs = value;
+    else if (key == 17) g_side_job = value;
 
     else return MORNA_ERR_INVALID_ARGUMENT;
     return MORNA_OK;

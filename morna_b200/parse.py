@@ -4,6 +4,7 @@ and query junction streams (search input).  Mirrors go_index's tokenising
 """
 import gzip
 import re
+import sys
 
 import numpy as np
 
@@ -222,13 +223,16 @@ def junctions_from_sam_stream(stream):
     for line in stream:
         if line[0] == "@":
             continue
-        tokens = line.strip().split("\t")
-        if len(tokens) < 10:
-            raise IndexError("Error found on line: " + line)
-        flag = int(tokens[1])
-        if flag & 4:
-            continue
-        rname, pos, cigar = tokens[2], int(tokens[3]), tokens[5]
+        try:                                   # utils.py:268-290: a short line prints to stderr, then the IndexError propagates
+            tokens = line.strip().split("\t")
+            flag = int(tokens[1])
+            if flag & 4:                       # unmapped reads are skipped before any other column is touched
+                continue
+            rname, cigar, pos = tokens[2], tokens[5], int(tokens[3])
+            tokens[9]                          # the reference reads SEQ here
+        except IndexError:
+            sys.stderr.write("Error found on line: " + line + "\n")
+            raise
         if "N" not in cigar or flag & 256:
             continue
         if _CIGAR_OP.sub("", cigar):

@@ -3,6 +3,7 @@ exact scan running on the B200.  Loads basename.stats/.freq/.map.mor and the vec
 store, keeps the float32 sample matrix resident in HBM, and answers exact angular
 top-k queries under the reference's order (distance ascending, ties id-descending).
 """
+import ctypes
 import math
 import os
 from collections import defaultdict
@@ -63,7 +64,6 @@ class MornaSearch(object):
         self._load_rows(host)
         self.query = defaultdict(int)                      # morna.py:540
         self.query_sample = [0.0] * self.dim               # :541
-        self._ws = None
 
     def _load_rows(self, host):
         n = self.row_hi - self.row_lo
@@ -128,59 +128,102 @@ class MornaSearch(object):
             self.query_sample[b] += s * (self.query[j] * idf)
 
     # ------------------------------------------------------------------ exact search
-    def _workspace(self, nbytes):
-        if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = _lib.workspace(nbytes, self.device)
-        return self._ws
+    def _workspace(self, nbytes, kind="exact"):
+        """Scratch of the CURRENT stream: calls in flight on different streams never share a workspace."""
+        pool = self.__dict__.setdefault("_ws_pool", {})
+        key = (kind, torch.cuda.current_stream(self.device).cuda_stream)
+        ws = pool.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = pool[key] = _lib.workspace(nbytes, self.device)
+            if kind == "single":
+                _lib.check(self.lib.morna_knn_single_workspace_init(_lib.dev_ptr(ws), ws.numel(), _lib.stream_ptr()),
+                           "morna_knn_single_workspace_init")
+                pool[("single_flag", key[1])] = torch.zeros(1, dtype=torch.int32, device=self.device)
+        return ws
 
     def single_search_device(self, query, k, stream=None):
-        """One query (CUDA float64 [dim]) through the HBM-bound FP32 scan + FP64 re-rank.
-        Same results as the FP64 scan; falls back to it when ties overflow the candidate list."""
+        """One query (CUDA float64 [dim]) through the HBM-bound single-query kernel.  Same results as the
+        FP64 scan; falls back to it when ties overflow the candidate list.  Everything (allocations, kernels,
+        the read of the fallback flag) happens on ``stream`` (default: the current stream)."""
         assert query.is_cuda and query.dtype == torch.float64 and query.numel() == self.dim
+        if stream is not None and stream != torch.cuda.current_stream(self.device):
+            with torch.cuda.stream(stream):
+                return self.single_search_device(query, k)
         query = query.contiguous()
         n, dev = self.row_hi - self.row_lo, self.device
-        out_ids = torch.empty((1, k), dtype=torch.int32, device=dev)
-        out_d = torch.empty((1, k), dtype=torch.float64, device=dev)
-        if n == 0 or k > 512:
-            return self.exact_search_device(query.view(1, -1), k, stream, allow_single=False)
+        k_eff = min(int(k), n)
+        if n == 0 or k_eff <= 0 or k_eff > 512:
+            return self.exact_search_device(query.view(1, -1), k, allow_single=False)
+        out_ids = torch.full((1, k), -1, dtype=torch.int32, device=dev)
+        out_d = torch.full((1, k), float("inf"), dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
-            need = self.lib.morna_knn_single_workspace_bytes(n)
-            if getattr(self, "_sws", None) is None or self._sws.numel() < need:
-                self._sws = _lib.workspace(need, dev)
-                self._sfallback = torch.zeros(1, dtype=torch.int32, device=dev)
-                _lib.check(self.lib.morna_knn_single_workspace_init(_lib.dev_ptr(self._sws), self._sws.numel(),
-                                                                    _lib.stream_ptr(stream)), "morna_knn_single_workspace_init")
+            sws = self._workspace(self.lib.morna_knn_single_workspace_bytes(n), "single")
+            flag = self._ws_pool[("single_flag", torch.cuda.current_stream(dev).cuda_stream)]
+            self._sws, self._sfallback = sws, flag            # (kept for callers that replay the call, e.g. bench.py)
             _lib.check(self.lib.morna_knn_single(
                 _lib.dev_ptr(self.vectors), _lib.dev_ptr(self.pp), n, self.dim, self.ld, self.row_lo,
-                _lib.ptr(query), k, _lib.dev_ptr(out_ids), _lib.dev_ptr(out_d), _lib.dev_ptr(self._sfallback),
-                _lib.dev_ptr(self._sws), self._sws.numel(), _lib.stream_ptr(stream)), "morna_knn_single")
-            if int(self._sfallback.item()):
-                return self.exact_search_device(query.view(1, -1), k, stream, allow_single=False)
+                _lib.ptr(query), k_eff, _lib.dev_ptr(out_ids), _lib.dev_ptr(out_d), _lib.dev_ptr(flag),
+                _lib.dev_ptr(sws), sws.numel(), _lib.stream_ptr()), "morna_knn_single")
+            if int(flag.item()):
+                return self.exact_search_device(query.view(1, -1), k, allow_single=False)
         return out_ids, out_d
 
+    MAX_SELECT_K = 2048              # kSelMaxK of morna_select_topk
+
     def exact_search_device(self, queries, k, stream=None, allow_single=True):
-        """queries: CUDA float64 [nq x dim] (row stride = queries.stride(0)).  Returns
-        device (ids int32 [nq x k], dists float64 [nq x k]); ids are global internal
-        ids (row_lo + local row); short lists are padded with id -1 / +inf."""
+        """queries: CUDA float64 [nq x dim].  Returns device (ids int32 [nq x k], dists float64 [nq x k]); ids are
+        global internal ids (row_lo + local row); short lists are padded with id -1 / +inf.  Like the reference's
+        exact_search_nn (morna.py:681-712) any k is served: k above the number of rows returns every row, k <= 0
+        an empty list."""
         assert queries.is_cuda and queries.dtype == torch.float64 and queries.dim() == 2
+        if stream is not None and stream != torch.cuda.current_stream(self.device):
+            with torch.cuda.stream(stream):
+                return self.exact_search_device(queries, k, allow_single=allow_single)
         queries = queries.contiguous()
         nq = queries.shape[0]
         q_ld = queries.shape[1]            # (a size-1 leading dimension may report stride 0)
         assert q_ld == self.dim, "queries must be [nq x dim]"
         n = self.row_hi - self.row_lo
         dev = self.device
+        k = max(int(k), 0)
         out_ids = torch.full((nq, k), -1, dtype=torch.int32, device=dev)
         out_d = torch.full((nq, k), float("inf"), dtype=torch.float64, device=dev)
-        if n == 0 or nq == 0:
+        k_eff = min(k, n)
+        if n == 0 or nq == 0 or k_eff == 0:
             return out_ids, out_d
-        if nq == 1 and allow_single:
-            return self.single_search_device(queries[0], k, stream)
+        if nq == 1 and allow_single and k_eff <= 512:
+            return self.single_search_device(queries[0], k)
         with torch.cuda.device(dev):
-            ws = self._workspace(self.lib.morna_knn_exact_workspace_bytes(n, nq, k))
+            if k_eff > self.MAX_SELECT_K:
+                return self._full_sort_search(queries, k, out_ids, out_d)
+            ws = self._workspace(self.lib.morna_knn_exact_workspace_bytes(n, nq, k_eff))
+            ids_k = out_ids if k_eff == k else torch.empty((nq, k_eff), dtype=torch.int32, device=dev)
+            d_k = out_d if k_eff == k else torch.empty((nq, k_eff), dtype=torch.float64, device=dev)
             _lib.check(self.lib.morna_knn_exact(
                 _lib.dev_ptr(self.vectors), _lib.dev_ptr(self.pp), n, self.dim, self.ld, self.row_lo,
-                _lib.ptr(queries), nq, q_ld, k, _lib.dev_ptr(out_ids), _lib.dev_ptr(out_d),
-                _lib.dev_ptr(ws), ws.numel(), _lib.stream_ptr(stream)), "morna_knn_exact")
+                _lib.ptr(queries), nq, q_ld, k_eff, _lib.dev_ptr(ids_k), _lib.dev_ptr(d_k),
+                _lib.dev_ptr(ws), ws.numel(), _lib.stream_ptr()), "morna_knn_exact")
+            if k_eff != k:
+                out_ids[:, :k_eff] = ids_k
+                out_d[:, :k_eff] = d_k
+        return out_ids, out_d
+
+    def _full_sort_search(self, queries, k, out_ids, out_d):
+        """k beyond the select kernel's list size (2048): all distances (morna_angular_distances, the canonical FP64
+        sums) and a full device sort per query under the reference order -- rare (a user asking for thousands of
+        neighbours), so the sort is torch's."""
+        n, dev = self.row_hi - self.row_lo, self.device
+        k_eff = min(k, n)
+        dist = torch.empty(n, dtype=torch.float64, device=dev)
+        for j in range(queries.shape[0]):
+            _lib.check(self.lib.morna_angular_distances(
+                _lib.dev_ptr(self.vectors), _lib.dev_ptr(self.pp), n, self.dim, self.ld, _lib.ptr(queries[j]), 1, self.dim,
+                _lib.dev_ptr(dist), n, _lib.stream_ptr()), "morna_angular_distances")
+            # distance ascending, equal distances id descending: stable sort of the id-reversed array
+            order = torch.sort(dist.flip(0), stable=True).indices[:k_eff]
+            rows = (n - 1) - order
+            out_ids[j, :k_eff] = (rows + self.row_lo).to(torch.int32)
+            out_d[j, :k_eff] = dist[rows]
         return out_ids, out_d
 
     # ------------------------------------------------------------------ batched search (tensor cores)
@@ -242,7 +285,7 @@ class MornaSearch(object):
                 sub = MornaSearch.__new__(MornaSearch)
                 sub.__dict__.update(self.__dict__)
                 sub.vectors, sub.pp = self.vectors[b0:b1], self.pp[b0:b1]
-                sub.row_lo, sub.row_hi, sub._ws = self.row_lo + b0, self.row_lo + b1, None
+                sub.row_lo, sub.row_hi, sub._ws_pool = self.row_lo + b0, self.row_lo + b1, {}
                 e_ids, e_d = sub.exact_search_device(queries[idx], k, stream, allow_single=False)
                 out_ids[idx] = e_ids
                 out_d[idx] = e_d
@@ -263,7 +306,7 @@ class MornaSearch(object):
         nq = queries.shape[0]
         n = self.row_hi - self.row_lo
         assert queries.shape[1] == self.dim
-        if n == 0 or nq == 0 or k > 512:
+        if n == 0 or nq == 0 or k > 512 or k <= 0 or k > n:
             return self.exact_search_device(queries, k, stream)
         parts = self._batched_launch(queries, k, stream, phase_events)
         if check_overflow:
@@ -362,23 +405,29 @@ class _PipeSlot(object):
 
 class BatchPipeline(object):
     """``depth`` query batches in flight on one MornaSearch (see MornaSearch.search_batches).
-    submit() enqueues pinned-host -> device copy, the batched search and the device -> pinned-host copy
-    of ids, distances and the overflow counters on the slot's stream and returns at once; collect()
-    waits for the oldest batch and returns host arrays (views of the slot's pinned buffers, valid until
-    the slot is reused ``depth`` submits later)."""
+
+    All kernels run on ONE compute stream; every slot has a copy stream for its pinned-host -> device and
+    device -> pinned-host transfers, which overlap the other batches' kernels.  The scoring call of batch
+    i+1 carries the re-rank of batch i as its side job (helper warps inside the tcgen05 GEMM kernels, see
+    morna_knn_batched_score), so a batch's results are completed when the next batch is submitted -- or at
+    collect() if nothing followed.  submit() returns at once; collect() waits for the oldest batch and returns
+    host arrays (views of the slot's pinned buffers, valid until the slot is reused ``depth`` submits later)."""
 
     def __init__(self, search, k, depth=2):
         self.search, self.k, self.depth = search, k, depth
         search.enable_tensor_path()
+        dev = search.device
+        self.compute = torch.cuda.Stream(device=dev)
         self.slots = []
         for _ in range(depth):
             sl = _PipeSlot()
-            sl.stream = torch.cuda.Stream(device=search.device)
-            sl.done = torch.cuda.Event()
+            sl.stream = torch.cuda.Stream(device=dev)        # this slot's copies
+            sl.h2d, sl.scored, sl.ranked, sl.done = (torch.cuda.Event() for _ in range(4))
             sl.nq = -1
-            sl.host_q = None
+            sl.host_q = sl.ws = sl.job = sl.parts = None
             self.slots.append(sl)
         self.head = self.tail = 0           # next slot to submit into / to collect from
+        self.unranked = None                # the slot whose candidate lists wait for their re-rank
 
     def _size(self, sl, nq, dtype, staging):
         s, k = self.search, self.k
@@ -387,9 +436,51 @@ class BatchPipeline(object):
         if sl.nq == nq:
             return
         sl.nq = nq
+        dev = s.device
         sl.host_ids = torch.empty((nq, k), dtype=torch.int32).pin_memory()
         sl.host_d = torch.empty((nq, k), dtype=torch.float64).pin_memory()
-        sl.host_stats = torch.empty((1 + (s.row_hi - s.row_lo - 1) // s.BATCH_BLOCK_ROWS, 4), dtype=torch.int32).pin_memory()
+        sl.host_stats = torch.empty((1 + max(s.row_hi - s.row_lo - 1, 0) // s.BATCH_BLOCK_ROWS, 4), dtype=torch.int32).pin_memory()
+        sl.ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+        sl.d = torch.empty((nq, k), dtype=torch.float64, device=dev)
+        sl.overflow = torch.empty(max(nq, 1), dtype=torch.uint8, device=dev)
+        sl.stats = torch.empty(4, dtype=torch.int32, device=dev)
+
+    def _score(self, sl, side):
+        """Scoring half of the slot's batch on the compute stream (current); `side`: slot whose re-rank rides along."""
+        s, k, lib = self.search, self.k, self.search.lib
+        n = s.row_hi - s.row_lo
+        need = lib.morna_knn_batched_workspace_bytes(n, sl.nq, s.dim, k)
+        if sl.ws is None or sl.ws.numel() < need:
+            sl.ws = _lib.workspace(need, s.device)
+        job = ctypes.byref(side.job) if side is not None else None
+        _lib.check(lib.morna_knn_batched_score(
+            _lib.dev_ptr(s.hs), s.ld_h, _lib.dev_ptr(s.rho_max), n, s.dim, s.row_lo, _lib.ptr(sl.qd), sl.nq, s.dim, k,
+            _lib.dev_ptr(sl.overflow), _lib.dev_ptr(sl.stats), _lib.dev_ptr(sl.ws), sl.ws.numel(), None, job,
+            _lib.stream_ptr()), "morna_knn_batched_score")
+        sl.job = _lib.RerankJob(s.vectors.data_ptr(), s.pp.data_ptr(), n, s.dim, s.ld, s.row_lo, sl.qd.data_ptr(), sl.nq, s.dim, k,
+                                sl.overflow.data_ptr(), sl.ws.data_ptr(), sl.ws.numel())
+
+    def _rerank(self, sl, resume):
+        """Re-rank half (what the helper warps left of it when `resume`) on the compute stream, then the slot's
+        device -> host copies on its copy stream."""
+        s, k, lib = self.search, self.k, self.search.lib
+        j = sl.job
+        _lib.check(lib.morna_knn_batched_rerank(
+            j.vectors, j.pp, j.n, j.dim, j.ld, j.id_base, j.queries, j.nq, j.q_ld, j.k, _lib.dev_ptr(sl.ids),
+            _lib.dev_ptr(sl.d), j.overflow, j.workspace, j.workspace_bytes, 1 if resume else 0, _lib.stream_ptr()),
+            "morna_knn_batched_rerank")
+        sl.ranked.record()
+        self._copy_back(sl, sl.ids, sl.d, [sl.stats])
+
+    def _copy_back(self, sl, ids, d, stats):
+        sl.stream.wait_event(sl.ranked)
+        with torch.cuda.stream(sl.stream):
+            for i, st in enumerate(stats):
+                sl.host_stats[i].copy_(st, non_blocking=True)
+            if ids is not None:
+                sl.host_ids.copy_(ids, non_blocking=True)
+                sl.host_d.copy_(d, non_blocking=True)
+            sl.done.record(sl.stream)
 
     def submit(self, queries):
         s, k = self.search, self.k
@@ -411,35 +502,56 @@ class BatchPipeline(object):
             sl.stream.wait_stream(torch.cuda.current_stream(s.device))             # the caller's writes to q are done
         with torch.cuda.stream(sl.stream):
             sl.qd = src.to(s.device, non_blocking=True).to(torch.float64).contiguous()   # float32 widens exactly
-            n = s.row_hi - s.row_lo
-            if n == 0 or sl.nq == 0 or k > 512:
-                sl.parts = None
+            sl.h2d.record(sl.stream)
+        n = s.row_hi - s.row_lo
+        self.compute.wait_event(sl.h2d)
+        with torch.cuda.stream(self.compute):
+            prev, self.unranked = self.unranked, None
+            sl.parts = sl.job = None
+            sl.mode = "plain"
+            if n == 0 or sl.nq == 0 or k > 512 or k <= 0 or k > n:
+                if prev is not None:
+                    self._rerank(prev, resume=False)
                 ids, d = s.exact_search_device(sl.qd, k)
-            else:
+                sl.keep = (ids, d)
+                sl.ranked.record()
+                self._copy_back(sl, ids, d, [])
+            elif n > s.BATCH_BLOCK_ROWS:     # several row blocks: every block is scored and re-ranked here, merged at collect()
+                if prev is not None:
+                    self._rerank(prev, resume=False)
+                sl.mode = "blocks"
                 sl.parts = s._batched_launch(sl.qd, k)
-                for i, part in enumerate(sl.parts):
-                    sl.host_stats[i].copy_(part[5], non_blocking=True)
-                ids, d = sl.parts[0][2], sl.parts[0][3]
-            sl.simple = sl.parts is None or len(sl.parts) == 1
-            if sl.simple:
-                sl.host_ids.copy_(ids, non_blocking=True)
-                sl.host_d.copy_(d, non_blocking=True)
-            sl.done.record(sl.stream)
+                sl.ranked.record()
+                self._copy_back(sl, None, None, [part[5] for part in sl.parts])
+            else:
+                sl.mode = "pipelined"
+                self._score(sl, prev if (prev is not None and self.depth > 1) else None)
+                if prev is not None:
+                    self._rerank(prev, resume=self.depth > 1)
+                self.unranked = sl
 
     def collect(self):
         s, k = self.search, self.k
         assert self.tail < self.head, "nothing in flight"
         sl = self.slots[self.tail % self.depth]
         self.tail += 1
+        if self.unranked is sl:              # nothing was submitted after it: its re-rank runs on its own
+            self.unranked = None
+            with torch.cuda.stream(self.compute):
+                self._rerank(sl, resume=False)
         sl.done.synchronize()
-        if sl.parts is not None:
-            overflowed = int(sl.host_stats[:len(sl.parts), 0].sum()) > 0
-            if overflowed or not sl.simple:  # rare: exact-scan fix-up and/or merge of row blocks, then copy again
-                with torch.cuda.stream(sl.stream):
-                    ids, d = s._batched_finish(sl.parts, sl.qd, k, host_stats=[sl.host_stats[i] for i in range(len(sl.parts))])
-                    sl.host_ids.copy_(ids, non_blocking=True)
-                    sl.host_d.copy_(d, non_blocking=True)
-                sl.stream.synchronize()
-            else:
-                s.last_stats = sl.host_stats[0].to(torch.int64).tolist()
+        if sl.mode == "plain":
+            return sl.host_ids.numpy(), sl.host_d.numpy()
+        if sl.mode == "pipelined":
+            sl.parts = [(0, s.row_hi - s.row_lo, sl.ids, sl.d, sl.overflow, sl.stats)]
+        nparts = len(sl.parts)
+        overflowed = int(sl.host_stats[:nparts, 0].sum()) > 0
+        if overflowed or nparts > 1:         # rare: exact-scan fix-up and/or merge of row blocks, then copy again
+            with torch.cuda.stream(self.compute):
+                ids, d = s._batched_finish(sl.parts, sl.qd, k, host_stats=[sl.host_stats[i] for i in range(nparts)])
+                sl.host_ids.copy_(ids, non_blocking=True)
+                sl.host_d.copy_(d, non_blocking=True)
+            self.compute.synchronize()
+        else:
+            s.last_stats = sl.host_stats[0].to(torch.int64).tolist()
         return sl.host_ids.numpy(), sl.host_d.numpy()

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name + " declared in include/morna_b200.h but not exported"
     assert set(declared) == set(_lib.EXPORTED_SYMBOLS), "ctypes table and header disagree"
-    assert _lib.load().morna_abi_version() == 1
+    assert _lib.load().morna_abi_version() == _lib.ABI_VERSION == 2
     assert _lib.load().morna_status_string(-2) == b"workspace too small"
 
 
@@ -119,6 +119,17 @@ def test_query_stream_parsers():
            "r3\t256\tchr2\t1000\t60\t10M100N5M\t*\t0\t0\tACGT\t*\n"
            "r4\t0\tchr2\t1000\t60\t25M\t*\t0\t0\tACGT\t*\n")
     assert list(parse.junctions_from_sam_stream(io.StringIO(sam))) == [("chr2", 1010, 1109, 1), ("chr2", 1120, 1169, 1)]
+
+
+def test_sam_short_lines_behave_like_the_reference(capsys):
+    """utils.py:268-290: an unmapped read is skipped before any other column is read (short lines included); a short
+    mapped line prints 'Error found on line' to stderr and the IndexError propagates."""
+    ok = "r1\t4\tchr2\n" + "r2\t0\tchr2\t1000\t60\t10M100N5M\t*\t0\t0\tACGT\t*\n"
+    assert list(parse.junctions_from_sam_stream(io.StringIO(ok))) == [("chr2", 1010, 1109, 1)]
+    bad = "r3\t0\tchr2\t1000\t60\t10M100N5M\n"
+    with pytest.raises(IndexError):
+        list(parse.junctions_from_sam_stream(io.StringIO(bad)))
+    assert "Error found on line: r3" in capsys.readouterr().err
 
 
 def test_cli_parser_defaults_match_reference():
