@@ -8,9 +8,17 @@ A step = one batch of 4096 queries answered exactly (ids + distances) against th
 HBM-resident sample matrix.  N > 1 (torchrun, one rank per GPU): every rank holds the
 50k-row matrix and answers its own 4096-query batch -- queries are independent, so
 there is no data-path collective; per-GPU work is fixed (weak scaling) and `value`
-is all ranks' queries / max-over-ranks device time.  `--rows-sharded` runs the other
-multi-GPU mode instead (rows split across ranks, NCCL all-gather + merge of top-k).
-Prints ONE JSON line on rank 0.
+is all ranks' queries / max-over-ranks device time.
+
+The same run also measures, and reports as extra keys of the ONE JSON line rank 0 prints:
+  rows_sharded   BASELINE configs[3]: 1,000,000 x 3000 rows split over the N ranks, the queries replicated, one NCCL
+                 all-gather of score bounds and one all-gather of the top-k lists + merge INSIDE the timed region (N = 1:
+                 the whole matrix on the one GPU, so strong scaling is computable from the per-N lines)
+  datasets       the headline step on clustered ("tissue") and intropolis-like sparse, tie-heavy rows
+  single_query   BASELINE configs[1]: 21,504 x 3000, one query, HBM roofline, and its end-to-end latency
+  index_build    BASELINE configs[4]: scatter-add of 500 M (sample, coverage) pairs, --features swept
+  cpu_baseline   the C port of the reference's loop on all host cores, the literal Python loop, a strong CPU
+                 baseline (torch FP32 GEMM + top-k + FP64 re-rank on all cores), Annoy "n/a"
 """
 import argparse
 import json
@@ -25,6 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_SAMPLES, DIM, N_QUERIES, K = 50000, 3000, 4096, 100
+N_SHARDED = 1000000
 METRIC = "exact kNN queries/s (50k samples x 3000 feats, k=100)"
 
 
@@ -55,7 +64,7 @@ class ClockSampler(threading.Thread):
             while not self._stop_evt.is_set():
                 self.rows.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
                                   nv.nvmlDeviceGetCurrentClocksEventReasons(h), nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
-                time.sleep(0.005)
+                time.sleep(0.002)
         except Exception as exc:      # NVML absent: report that instead of clocks
             self.error = "nvml_unavailable:%s" % type(exc).__name__
 
@@ -73,12 +82,7 @@ class ClockSampler(threading.Thread):
                 "power_w": float(np.mean([r[3] for r in rows])) if rows else None}
 
 
-def synth_matrix(torch, device, n, dim, seed):
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    return torch.randn((n, dim), generator=g, device=device, dtype=torch.float32)
-
-
+# ---------------------------------------------------------------------------------------------- CPU baselines
 def cpu_baseline_run(n_samples, dim, k, n_queries, threads, seed=1234):
     """Times the C port of exact_search_nn (oracle/oracle.c) on `n_queries` queries of the
     same workload, queries split over `threads` host threads.  Returns queries/s."""
@@ -107,11 +111,39 @@ def literal_reference_qps(dim, n_samples, rows=300, seed=1):
     return 1.0 / (dt * n_samples / rows)
 
 
-def workload_config(n_samples, nq, world, rows_sharded):
+def strong_cpu_qps(n_samples, dim, k, n_queries, seed=1234):
+    """what a CPU can do with the same idea -- torch FP32 S @ Q^T on all cores, top-(k+32) per query,
+    FP64 re-rank of those candidates.  Not the reference's algorithm and not exact by construction; context only."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(seed)
+    S = torch.randn((n_samples, dim), generator=g)
+    rows = torch.randperm(n_samples, generator=g)[:n_queries]
+    Q = S[rows]
+    Sn = S / S.norm(dim=1, keepdim=True)
+    t0 = time.perf_counter()
+    Qn = Q / Q.norm(dim=1, keepdim=True)
+    scores = Qn @ Sn.t()
+    cand = scores.topk(k + 32, dim=1).indices
+    S64 = S.double()
+    out = torch.empty((n_queries, k), dtype=torch.int64)
+    for j in range(n_queries):
+        c = cand[j]
+        rowsj = S64[c]
+        qj = Q[j].double()
+        cos = (rowsj @ qj) / (rowsj.norm(dim=1) * qj.norm())
+        d = (2 - 2 * cos).clamp_min(0).sqrt()
+        out[j] = c[torch.argsort(d, stable=True)[:k]]
+    dt = time.perf_counter() - t0
+    assert bool((out[:, 0] == rows).all())
+    return n_queries / dt, dt, cores
+
+
+def workload_config(n_samples, nq, world):
     return {"workload": "%d samples x %d features (gaussian, seed 1234), %d in-index queries per GPU per step, "
                         "exact top-%d ids+distances" % (n_samples, DIM, nq, K),
-            "parallelism": ("rows-sharded x%d + NCCL all-gather merge" % world) if rows_sharded
-                           else ("replicated index, queries sharded x%d" % world),
+            "parallelism": "replicated index, queries sharded x%d" % world,
             "l2": "inputs larger than L2 (sample matrix %.0f MB)" % (n_samples * DIM * 4 / 1e6)}
 
 
@@ -133,12 +165,33 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(N_SAMPLES, N_QUERIES, 1, False),
+            "config": workload_config(N_SAMPLES, N_QUERIES, 1),
             "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
                              "sample": "%d of the 4096 queries per step x %d steps, C port of exact_search_nn (morna.py:681-712; the "
                                        "reference itself is Python 2 + annoy and cannot run here), one thread per core" % (per_step, args.steps)},
             "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def pipeline_ms(torch, srch, batches, k, depth=2):
+    """`len(batches)` batches through MornaSearch.search_batches; device time per batch (CUDA events on the current
+    stream, which waits for the pipeline's streams)."""
+    dev = srch.device
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    got, last = 0, None
+    for ids, d in srch.search_batches(iter(batches), k, depth=depth):
+        got, last = got + 1, (ids, d)
+    pipe = srch._pipes[(k, depth)]
+    cur = torch.cuda.current_stream(dev)
+    for sl in pipe.slots:
+        cur.wait_stream(sl.compute)
+        cur.wait_stream(sl.stream)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    assert got == len(batches)
+    return e0.elapsed_time(e1) / len(batches), last
 
 
 def main():
@@ -147,10 +200,12 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rows-sharded", action="store_true", help="split rows across ranks + NCCL top-k merge")
     ap.add_argument("--samples", type=int, default=N_SAMPLES)
     ap.add_argument("--queries", type=int, default=N_QUERIES)
+    ap.add_argument("--sharded-rows", type=int, default=N_SHARDED, help="rows of the rows-sharded section (0 = skip it)")
+    ap.add_argument("--index-pairs", type=float, default=500e6, help="pairs of the index-build section (0 = skip it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only-headline", action="store_true", help="skip every extra section")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -162,7 +217,7 @@ def main():
 
     import torch
     import torch.distributed as td
-    from morna_b200 import _lib, dist as mdist
+    from morna_b200 import _lib, synth
     from morna_b200.search import MornaSearch
     _lib.require_cuda()
     torch.cuda.set_device(local_rank)
@@ -171,171 +226,231 @@ def main():
         td.init_process_group("nccl", device_id=device)
     lib = _lib.load()
     n_samples, nq = args.samples, args.queries
-
-    # ---- synthetic index, resident in HBM
-    if args.rows_sharded and world > 1:
-        lo, hi = mdist.shard_bounds(n_samples, rank, world)
-        S = synth_matrix(torch, device, hi - lo, DIM, 1234 + rank)
-        srch = MornaSearch(vectors=S, stats=(n_samples, hi - lo, DIM), device=device)
-        srch.row_lo, srch.row_hi = lo, hi                   # global ids of this block
-        qgen = torch.Generator(device=device); qgen.manual_seed(99)
-        queries64 = torch.randn((nq, DIM), generator=qgen, device=device, dtype=torch.float32).to(torch.float64)
-    else:
-        S = synth_matrix(torch, device, n_samples, DIM, 1234)
-        srch = MornaSearch(vectors=S, stats=(n_samples, n_samples, DIM), device=device)
-        qg = torch.Generator(device="cpu"); qg.manual_seed(99 + rank)
-        rows = torch.randperm(n_samples, generator=qg)[:nq].to(device)
-        queries64 = S[rows].to(torch.float64)               # in-index queries (float32-valued)
-    del S
-    host_q = queries64.to(torch.float32).cpu().pin_memory()      # the queries are float32-valued rows
-    host_ids = torch.empty((nq, K), dtype=torch.int32).pin_memory()
-    host_d = torch.empty((nq, K), dtype=torch.float64).pin_memory()
-
-    srch.enable_tensor_path()
-
-    def step_resident():
-        ids, d = srch.batched_search_device(queries64, K)
-        if args.rows_sharded and world > 1:
-            gi, gd = mdist.all_gather_sorted(ids, d)
-            ids, d = mdist.merge_sorted_lists(gi, gd, K)
-        return ids, d
-
-    def step_e2e():
-        """One batch through the synchronous host call: pinned host queries in, host results out."""
-        q = host_q.to(device, non_blocking=True).to(torch.float64)   # widened exactly on the device
-        ids, d = srch.batched_search_device(q, K)
-        if args.rows_sharded and world > 1:
-            gi, gd = mdist.all_gather_sorted(ids, d)
-            ids, d = mdist.merge_sorted_lists(gi, gd, K)
-        host_ids.copy_(ids, non_blocking=True)
-        host_d.copy_(d, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-
-    def run_e2e(steps):
-        """`steps` batches end to end.  Replicated index: MornaSearch.search_batches (the streaming host
-        API: two batches in flight, every batch's pinned host->device copy of its 4096 queries and the
-        device->host copy of its ids + distances are inside the timed region and overlap the previous
-        batch's kernels).  Rows-sharded: the synchronous call per batch (the all-gather orders the ranks)."""
-        if args.rows_sharded and world > 1:
-            for _ in range(steps):
-                step_e2e()
-            return
-        got = 0
-        for ids, d in srch.search_batches((host_q for _ in range(steps)), K, depth=2):
-            got += 1
-        assert got == steps and int(ids[0, 0]) == int(rows[0])
+    peaks = measured_peaks()
 
     def barrier():
         if world > 1:
             td.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- synthetic index, resident in HBM; every rank its own queries
+    S = synth.gauss(n_samples, DIM, device, 1234)
+    srch = MornaSearch(vectors=S, stats=(n_samples, n_samples, DIM), device=device)
+    queries64, rows = synth.queries(S, nq, seed=99 + rank)          # in-index queries (float32-valued)
+    del S
+    host_q = queries64.to(torch.float32).cpu().pin_memory()          # the queries are float32-valued rows
+    srch.enable_tensor_path()
+
     sampler = ClockSampler(local_rank); sampler.start()
     for _ in range(args.warmup):
-        ids, d = step_resident()
-    if not (args.rows_sharded and world > 1):
-        for _ids, _d in srch.search_batches((queries64 for _ in range(args.warmup)), K, depth=2):
-            pass
+        ids, d = srch.batched_search_device(queries64, K)
+    pipeline_ms(torch, srch, [queries64] * args.warmup, K)
     torch.cuda.synchronize()
-    if not (args.rows_sharded and world > 1):
-        assert torch.equal(ids[:, 0].long(), rows), "every in-index query must find itself first"
-        assert float(d[:, 0].abs().max()) == 0.0
+    assert torch.equal(ids[:, 0].long(), rows), "every in-index query must find itself first"
+    assert float(d[:, 0].abs().max()) == 0.0
 
-    # ---- timed region: K steps, inputs resident, CUDA events, max over ranks
+    # ---- timed region: K steps, inputs resident, CUDA events, max over ranks.  The streaming API on HBM-resident
+    # queries: batch i+1 is enqueued before batch i's overflow counters are read, so the host never stalls the device
     launches0 = _lib.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     wall0 = time.perf_counter()
-    ev0.record()
-    if args.rows_sharded and world > 1:
-        for _ in range(args.steps):
-            step_resident()
-    else:
-        # the streaming API on HBM-resident queries: batch i+1 is enqueued before batch i's overflow counters are
-        # read, so the host never stalls the device between batches (results still come back to the host)
-        got = 0
-        for _ids, _d in srch.search_batches((queries64 for _ in range(args.steps)), K, depth=2):
-            got += 1
-        assert got == args.steps
-        torch.cuda.current_stream().wait_stream(srch._pipes[(K, 2)].slots[0].stream)
-        torch.cuda.current_stream().wait_stream(srch._pipes[(K, 2)].slots[1].stream)
-    ev1.record()
+    ms_step, (last_ids, _last_d) = pipeline_ms(torch, srch, [queries64] * args.steps, K)
     barrier()
     wall1 = time.perf_counter()
-    ms_total = ev0.elapsed_time(ev1)
+    assert int(last_ids[0, 0]) == int(rows[0])
     launches = _lib.launch_count() - launches0
     clocks = sampler.window(wall0, wall1)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
-    if world > 1:
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-    ms_total = float(t.item())
-    job_queries = nq * (1 if (args.rows_sharded and world > 1) else world)
-    value = job_queries * args.steps / (ms_total / 1e3)
+    ms_step = max_over_ranks(ms_step)
+    value = nq * world / (ms_step / 1e3)
 
-    # ---- end to end through the host API: pinned host queries in, host results out
-    run_e2e(3)
+    # ---- end to end through the host API: pinned host queries in, host results out, copies inside the timed region
+    pipeline_ms(torch, srch, [host_q] * 3, K)
     barrier()
     t0 = time.perf_counter()
-    run_e2e(args.steps)
+    pipeline_ms(torch, srch, [host_q] * args.steps, K)
     barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-    if world > 1:
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-    e2e_value = job_queries * args.steps / float(t.item())
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = nq * world * args.steps / e2e_s
 
-    # ---- dominant kernel alone, CUDA events on its stream
-    peaks = measured_peaks()
+    # ---- dominant kernel alone, CUDA events on its stream; the step's own fraction beside it
     roofline = dominant_kernel_roofline(torch, lib, _lib, srch, queries64, peaks)
+    step_flops = 2.0 * nq * n_samples * DIM
+    roofline["step_frac"] = step_flops / (ms_step / 1e3) / 1e12 / peaks["bf16_tflops"]
+    roofline["step_frac_of_sustained"] = step_flops / (ms_step / 1e3) / 1e12 / peaks["bf16_tflops_sustained"]
+    roofline["step_algorithmic"] = "2*Q*N*D flops / ms_per_step (prep, thresholds, top-k and re-rank included), Q=%d N=%d D=%d" % (nq, n_samples, DIM)
 
-    single = None
-    if rank == 0 and not args.rows_sharded and n_samples == N_SAMPLES:
-        single = single_query_line(torch, lib, _lib, device, peaks)
+    extras = {}
+    full = not args.only_headline and n_samples == N_SAMPLES and nq == N_QUERIES
+    if full:
+        extras["datasets"] = dataset_lines(torch, synth, MornaSearch, device, rank, max_over_ranks, world)
+    del srch
+    torch.cuda.empty_cache()
+    if full and args.sharded_rows > 0:
+        extras["rows_sharded"] = rows_sharded_line(torch, td, synth, MornaSearch, device, rank, world, args.sharded_rows,
+                                                   max(5, min(args.steps, 10)), barrier, max_over_ranks)
+        torch.cuda.empty_cache()
+    single = index = None
+    if rank == 0 and full:
+        single = single_query_line(torch, lib, _lib, synth, device, peaks)
+        if args.index_pairs > 0:
+            torch.cuda.empty_cache()
+            index = index_build_line(torch, lib, _lib, device, peaks, args.index_pairs)
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             nq_cpu = min(N_QUERIES, 96 * cores)          # ~10 s of work on all host cores
             v, dt = cpu_baseline_run(N_SAMPLES, DIM, K, nq_cpu, cores)
+            sv, sdt, _ = strong_cpu_qps(N_SAMPLES, DIM, K, 1024)
             cpu = {"value": v, "unit": "queries/s", "cores": cores, "kind": "port",
                    "sample": "%d of the 4096 queries, C port of exact_search_nn (morna.py:681-712), %d threads, %.1f s"
                              % (nq_cpu, cores, dt),
                    "reference_as_written_qps": literal_reference_qps(DIM, N_SAMPLES),
                    "reference_as_written": "the literal pure-Python loop on one core, 300 rows timed and extrapolated to "
-                                           "50000 (the reference itself is Python 2 + annoy + mmh3 and cannot run here)"}
+                                           "50000 (the reference itself is Python 2 + annoy + mmh3 and cannot run here)",
+                   "strong_cpu": {"value": sv, "unit": "queries/s", "cores": cores, "sample": "1024 queries, %.1f s" % sdt,
+                                  "what": "torch FP32 S @ Q^T on all cores + top-(k+32) + FP64 re-rank of those candidates "
+                                          "(not the reference's algorithm, not exact by construction; context only)"},
+                   "annoy": "n/a (the annoy wheel is not installed and there is no network; the reference's approximate "
+                            "mode cannot be timed here)"}
         line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": roofline.pop("dtype"), "data": "synthetic",
-                "config": workload_config(n_samples, nq, world, args.rows_sharded),
+                "config": workload_config(n_samples, nq, world),
                 "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(host_q.numel() * host_q.element_size()),
-                        "d2h_bytes_per_step": int(host_ids.numel() * 4 + host_d.numel() * 8)},
+                        "d2h_bytes_per_step": int(nq * K * 4 + nq * K * 8)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "single_query": single,
-                "cpu_baseline": cpu,
-                "peaks": peaks["source"]}
+                "cpu_baseline": cpu, "peaks": peaks["source"]}
+        line.update(extras)
+        line["index_build"] = index
         print(json.dumps(line))
     if world > 1:
         td.destroy_process_group()
 
 
-def single_query_line(torch, lib, _lib, device, peaks):
+def dataset_lines(torch, synth, MornaSearch, device, rank, max_over_ranks, world, steps=8):
+    """The headline step on the other SURVEY 8(d) inputs: clustered rows with in- and out-of-index queries, and
+    intropolis-like sparse rows where thousands of rows tie (what the reference's own fixture looks like)."""
+    out = {}
+    for kind, noise in (("tissue", 0.0), ("tissue", 0.05), ("gauss", 0.05), ("sparse", 0.0)):
+        S = synth.matrix(kind, N_SAMPLES, DIM, device)
+        srch = MornaSearch(vectors=S, stats=(N_SAMPLES, N_SAMPLES, DIM), device=device)
+        q, _rows = synth.queries(S, N_QUERIES, seed=99 + rank, noise=noise)
+        del S
+        srch.enable_tensor_path()
+        pipeline_ms(torch, srch, [q] * 3, K)
+        ms, _ = pipeline_ms(torch, srch, [q] * steps, K)
+        ms = max_over_ranks(ms)
+        name = kind + ("_out_of_index" if noise else "_in_index")
+        out[name] = {"queries_per_s": N_QUERIES * world / (ms / 1e3), "ms_per_step": ms,
+                     "overflowed_queries": int(srch.last_stats[0]), "reranked_per_query": srch.last_stats[2] / N_QUERIES}
+        del srch, q
+        torch.cuda.empty_cache()
+    return out
+
+
+def rows_sharded_line(torch, td, synth, MornaSearch, device, rank, world, n_rows, steps, barrier, max_over_ranks):
+    """BASELINE configs[3]: n_rows x 3000 split into contiguous row blocks over the ranks (rank r draws its block from
+    seed 1234 + r), 4096 replicated queries per step, exact global top-100; the all-gather of the score bounds, the
+    all-gather of the lists and the merge are inside the timed region.  Strong scaling: the total work is fixed."""
+    from morna_b200 import dist as mdist
+    lo, hi = mdist.shard_bounds(n_rows, rank, world)
+    S = synth.gauss(hi - lo, DIM, device, 1234 + rank)
+    srch = MornaSearch(vectors=S, stats=(n_rows, hi - lo, DIM), device=device)
+    srch.row_lo, srch.row_hi = lo, hi                     # global ids of this block
+    del S
+    srch.enable_tensor_path()
+    q = synth.gauss(N_QUERIES, DIM, device, 99).to(torch.float64)       # the same out-of-index queries on every rank
+    host_q = q.to(torch.float32).cpu().pin_memory()
+    host_ids = torch.empty((N_QUERIES, K), dtype=torch.int32).pin_memory()
+    host_d = torch.empty((N_QUERIES, K), dtype=torch.float64).pin_memory()
+
+    def step(queries):
+        return mdist.sharded_batched_search(srch, queries, K, check_overflow=False)
+
+    def step_e2e():
+        qd = host_q.to(device, non_blocking=True).to(torch.float64)
+        ids, d = step(qd)
+        if rank == 0:
+            host_ids.copy_(ids, non_blocking=True)
+            host_d.copy_(d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        ids, d = step(q)
+    torch.cuda.synchronize()
+    assert int(srch.last_stats[0]) == 0 if srch.last_stats else True
+    assert bool((d[:, 1:] >= d[:, :-1]).all()) and int(ids.min()) >= 0 and int(ids.max()) < n_rows
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        step(q)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_e2e()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) / steps * 1e3)
+    # phases of one step on this rank (CUDA events around the calls of the sharded search)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    ev[0].record()
+    vals = srch.batched_score_bound(q, K); ev[1].record()
+    every = vals[None]
+    if world > 1:
+        every = torch.empty((world,) + tuple(vals.shape), dtype=vals.dtype, device=device)
+        td.all_gather_into_tensor(every, vals)
+    bound = srch.union_kth_bound(every, K)
+    ev[2].record()
+    li, ld_ = srch.batched_finish_bound(bound, check_overflow=False); ev[3].record()
+    if world > 1:
+        mdist.gather_merge_packed(li, ld_, K)
+    ev[4].record()
+    torch.cuda.synchronize()
+    phase = {n: round(ev[i].elapsed_time(ev[i + 1]), 4) for i, n in
+             enumerate(("score_to_local_bounds", "all_gather_bounds_kth", "final_lists_rerank_order", "all_gather_lists_merge"))}
+    stats = srch.last_stats
+    return {"workload": "%d samples x %d features in %d row blocks, %d replicated out-of-index queries per step, exact global top-%d"
+                        % (n_rows, DIM, world, N_QUERIES, K),
+            "value": N_QUERIES / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms, "steps": steps, "scaling": "strong",
+            "e2e": {"value": N_QUERIES / (e2e_ms / 1e3), "unit": "queries/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(host_q.numel() * 4), "d2h_bytes_per_step": int(N_QUERIES * K * 12)},
+            "collectives": ("all_gather of %d B (score bounds) + all_gather of %d B (top-k lists) per rank, NCCL"
+                            % (4 * N_QUERIES * K, 12 * N_QUERIES * K)) if world > 1 else "none (one rank)",
+            "rows_per_rank": hi - lo, "phase_ms": phase,
+            "tensor_frac": 2.0 * N_QUERIES * n_rows * DIM / (ms / 1e3) / 1e12 / world / measured_peaks()["bf16_tflops"]}
+
+
+def single_query_line(torch, lib, _lib, synth, device, peaks):
     """BASELINE configs[1]: one exact top-100 query over 21,504 x 3000 rows (the single-query kernel, HBM-bound:
     4*N*D algorithmic bytes per query), replayed back to back from a CUDA graph, CUDA events on the stream."""
     from morna_b200.search import MornaSearch
     n = 21504
-    S = synth_matrix(torch, device, n, DIM, 4321)
+    S = synth.gauss(n, DIM, device, 4321)
     srch = MornaSearch(vectors=S, stats=(n, n, DIM), device=device)
     q = S[n // 3].to(torch.float64).contiguous()
-    ids, d = srch.single_search_device(q, K)
-    assert int(ids[0, 0]) == n // 3 and float(d[0, 0]) == 0.0 and int(srch._sfallback.item()) == 0
-    out_i = torch.empty((1, K), dtype=torch.int32, device=device)
-    out_d = torch.empty((1, K), dtype=torch.float64, device=device)
-
-    def call():
-        _lib.check(lib.morna_knn_single(_lib.dev_ptr(srch.vectors), _lib.dev_ptr(srch.pp), n, DIM, srch.ld, 0, _lib.dev_ptr(q), K,
-                                        _lib.dev_ptr(out_i), _lib.dev_ptr(out_d), _lib.dev_ptr(srch._sfallback),
-                                        _lib.dev_ptr(srch._sws), srch._sws.numel(), _lib.stream_ptr()), "morna_knn_single")
     side = torch.cuda.Stream(device=device)
     with torch.cuda.stream(side):
+        ids, d = srch.single_search_device(q, K)
+        assert int(ids[0, 0]) == n // 3 and float(d[0, 0]) == 0.0 and int(srch._sfallback.item()) == 0
+        out_i = torch.empty((1, K), dtype=torch.int32, device=device)
+        out_d = torch.empty((1, K), dtype=torch.float64, device=device)
+
+        def call():
+            _lib.check(lib.morna_knn_single(_lib.dev_ptr(srch.vectors), _lib.dev_ptr(srch.pp), n, DIM, srch.ld, 0, _lib.dev_ptr(q), K,
+                                            _lib.dev_ptr(out_i), _lib.dev_ptr(out_d), _lib.dev_ptr(srch._sfallback),
+                                            _lib.dev_ptr(srch._sws), srch._sws.numel(), _lib.stream_ptr()), "morna_knn_single")
         for _ in range(3):
             call()
         graph = torch.cuda.CUDAGraph()
@@ -352,6 +467,15 @@ def single_query_line(torch, lib, _lib, device, peaks):
     side.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / reps
     assert torch.equal(out_i, ids) and torch.equal(out_d, d)
+    # end to end: host query in (pinned), host ids + distances out, one query at a time through the public call
+    hq = q.cpu().pin_memory()
+    for _ in range(5):
+        srch.exact_search_batch(hq.numpy()[None, :], K)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        hi_, hd_ = srch.exact_search_batch(hq.numpy()[None, :], K)
+    e2e_us = (time.perf_counter() - t0) / 50 * 1e6
+    assert int(hi_[0, 0]) == n // 3
     gbs = 4.0 * n * DIM / (us * 1e-6) / 1e9
     traffic = None
     prof = os.path.join(ROOT, "profiles", "r01_step_summary.json")     # dram bytes per launch from the committed ncu capture
@@ -359,9 +483,22 @@ def single_query_line(torch, lib, _lib, device, peaks):
         with open(prof) as fh:
             traffic = json.load(fh).get("scan64_dram_bytes_21504x3000")
     return {"workload": "21504 samples x 3000 features, one query, exact top-100 (the 258 MB matrix exceeds L2)",
-            "us_per_query": us, "queries_per_s": 1e6 / us, "kernel": "scan64_select_kernel<3,2> (one launch per query)",
+            "us_per_query": us, "queries_per_s": 1e6 / us, "kernel": "scan64_select_kernel (one launch per query)",
+            "e2e": {"us_per_query": e2e_us, "queries_per_s": 1e6 / e2e_us, "h2d_bytes": DIM * 8, "d2h_bytes": K * 12,
+                    "what": "MornaSearch.exact_search_batch with one host query: pinned copy in, kernel, ids + distances copied out, synchronous"},
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                         "traffic": traffic, "algorithmic": "4*N*D bytes per query"}}
+                         "traffic": traffic, "traffic_source": "static: dram__bytes_read+write of one launch in the committed ncu capture (profiles/), not measured in this run",
+                         "algorithmic": "4*N*D bytes per query"}}
+
+
+def index_build_line(torch, lib, _lib, device, peaks, pairs):
+    """BASELINE configs[4] through scripts/index_bench.py's generator: device time of id assignment, hashing, scatter-add
+    and float32 store for each --features value, against 8*nnz + 40*J + 4*N*D algorithmic bytes."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("index_bench", os.path.join(ROOT, "scripts", "index_bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.run(pairs=pairs, dims=(500, 1000, 3000, 10000, 30000), peak=peaks["hbm_gbs"], quiet=True)
 
 
 def dominant_kernel_roofline(torch, lib, _lib, srch, queries64, peaks):
@@ -427,6 +564,7 @@ def dominant_kernel_roofline(torch, lib, _lib, srch, queries64, peaks):
             "cublas_same_shape": None if lib_ms is None else {"ms": lib_ms, "tflops": 2.0 * nq * rows * ld_h / (lib_ms / 1e3) / 1e12,
                                                               "what": "torch.matmul fp16 %d x %d x %d, one launch at a time" % (nq, rows, ld_h)},
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": "static: dram__bytes_read+write of one launch in the committed ncu capture (profiles/), not measured in this run",
             "algorithmic": "2*Q*N*D flops per launch, Q=%d N=%d D=%d" % (nq, rows, srch.dim),
             "launch_ms": ms, "peak_source": peaks["source"] + " cuBLAS bf16 burst (fp16 runs on the same kind::f16 pipe)",
             "peak_sustained": peak_sustained, "frac_of_sustained": achieved / peak_sustained,

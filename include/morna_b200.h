@@ -252,7 +252,21 @@ typedef struct morna_rerank_job {
 int morna_knn_batched_score(const void *hs, int64_t ld_h, const float *rho_max, int64_t n, int32_t dim,
                             int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
                             uint8_t *overflow, int32_t *stats, void *workspace, size_t workspace_bytes,
-                            void *const *phase_events, const morna_rerank_job *side_job, void *stream);
+                            void *const *phase_events, const morna_rerank_job *side_job, float *kth_bound,
+                            void *stream);
+/* Rows-sharded search (one process per GPU, each holding a block of rows): give the scoring call a
+ * kth_bound [dev] float[nq * k]; instead of the final candidate lists it then writes, per query, lower bounds of the
+ * true cosines of its k best rows (score minus this rank's error bound; -inf pads a shorter list or an overflowed
+ * query).  The ranks all-gather these (4*nq*k bytes each, NCCL) and morna_union_kth_bound takes, per query, the k-th
+ * largest of the n_lists * k values: at least k rows over all shards have a true cosine at or above it.
+ * morna_knn_batched_finalize then builds each rank's candidate lists from that GLOBAL bound (rows scoring
+ * >= bound - eps of the rank): the ranks together re-rank about k rows per query, not k rows each.  Then
+ * morna_knn_batched_rerank as usual; the per-rank lists are merged with morna_merge_sorted_topk.
+ *   vals  [dev] float[n_lists * nq * k], layout [list][query][k] (what an all-gather leaves)
+ *   bound [dev] float[nq] out (-inf where fewer than k finite values exist) */
+int morna_union_kth_bound(const float *vals, int32_t n_lists, int64_t nq, int32_t k, float *bound, void *stream);
+int morna_knn_batched_finalize(int64_t n, int64_t nq, int32_t dim, int32_t k, const float *kth_bound,
+                               uint8_t *overflow, int32_t *stats, void *workspace, size_t workspace_bytes, void *stream);
 int morna_knn_batched_rerank(const float *vectors, const double *pp, int64_t n, int32_t dim, int64_t ld,
                              int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
                              int32_t *out_ids, double *out_dist, const uint8_t *overflow, void *workspace,

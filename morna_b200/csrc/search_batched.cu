@@ -152,7 +152,7 @@ struct RerankParams {
 // equal the exact scan's bit for bit.  Items are walked phase-major: with few rows and many queries
 // (rows re-ranked several times per batch) the row range of a phase stays L2-resident while all
 // queries pass over it; phases == 1 is the plain query-major gather.
-template <int kRows>
+template <int kRows, bool kPipe = false>
 __global__ void __launch_bounds__(kRrThreads)
 rerank_dist_kernel(const RerankParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -214,6 +214,50 @@ rerank_dist_kernel(const RerankParams p) {
 #pragma unroll
             for (int u = 0; u < kRows; ++u) acc[u] = 0.0;
             int c = lane;
+            if (kPipe) {
+                // software pipeline: the loads of chunk step i+1 are in flight while step i is accumulated (the plain loop
+                // below waits for all its loads, then computes with nothing in flight: ncu shows 9 of 10 issue slots lost
+                // to long-scoreboard stalls)
+                float4 va[kRows], vb[kRows];
+                if (c < chunks) {
+#pragma unroll
+                    for (int u = 0; u < kRows; ++u) va[u] = ldg_stream_f4(src[u] + c);
+                }
+                for (; c < chunks; c += 64) {
+                    const int c2 = c + 32, c3 = c + 64;
+                    if (c2 < chunks) {
+#pragma unroll
+                        for (int u = 0; u < kRows; ++u) vb[u] = ldg_stream_f4(src[u] + c2);
+                    }
+                    {
+                        const double2 qa = *reinterpret_cast<const double2 *>(qs + 4 * c);
+                        const double2 qb = *reinterpret_cast<const double2 *>(qs + 4 * c + 2);
+#pragma unroll
+                        for (int u = 0; u < kRows; ++u) {
+                            acc[u] = fma(f32_scaled_f64(va[u].x), qa.x, acc[u]);
+                            acc[u] = fma(f32_scaled_f64(va[u].y), qa.y, acc[u]);
+                            acc[u] = fma(f32_scaled_f64(va[u].z), qb.x, acc[u]);
+                            acc[u] = fma(f32_scaled_f64(va[u].w), qb.y, acc[u]);
+                        }
+                    }
+                    if (c3 < chunks) {
+#pragma unroll
+                        for (int u = 0; u < kRows; ++u) va[u] = ldg_stream_f4(src[u] + c3);
+                    }
+                    if (c2 < chunks) {
+                        const double2 qa = *reinterpret_cast<const double2 *>(qs + 4 * c2);
+                        const double2 qb = *reinterpret_cast<const double2 *>(qs + 4 * c2 + 2);
+#pragma unroll
+                        for (int u = 0; u < kRows; ++u) {
+                            acc[u] = fma(f32_scaled_f64(vb[u].x), qa.x, acc[u]);
+                            acc[u] = fma(f32_scaled_f64(vb[u].y), qa.y, acc[u]);
+                            acc[u] = fma(f32_scaled_f64(vb[u].z), qb.x, acc[u]);
+                            acc[u] = fma(f32_scaled_f64(vb[u].w), qb.y, acc[u]);
+                        }
+                    }
+                }
+                c = chunks;
+            }
             for (; c + 32 < chunks; c += 64) {
                 float4 v[2][kRows];
 #pragma unroll
@@ -813,6 +857,7 @@ struct KthParams {
     float *cand2_score; int32_t *cand2_id;        // refine mode: the compacted list goes here
     int32_t *fin_id; int32_t *fin_cnt;
     uint8_t *overflow; int32_t *stats;
+    float *kth_bound;                             // modes 3 / 4: per-query lower bound of the k-th best true cosine
 };
 
 // key of the kk-th largest of the keys one warp holds in registers (kItems per lane; 0 = padding)
@@ -844,10 +889,13 @@ constexpr int kKwSmem = kKwWarps * 2 * 32 * kKwSlots * (int)sizeof(uint32_t);   
 // found with warp-wide counts, and everything >= a_k - 2 eps is written out.  If the pivot misses
 // (too few survivors, a lane list overflows, or a_k - 2 eps falls below the pivot) the warp falls
 // back to a streaming bisection over all entries, which is exact for any input.
+//   kMode 3 (bound) : input = candidate list      -> kth_bound[q] = (k-th largest score) - eps, nothing emitted.  Rows-sharded
+//                     search: the maximum of this bound over the ranks is a lower bound of the GLOBAL k-th best cosine
+//   kMode 4 (emit)  : input = candidate list      -> final candidate list = everything >= kth_bound[q] - eps
 template <int kMode>
 __global__ void __launch_bounds__(kKwWarps * 32)
 kth_warp_kernel(KthParams p, int nq) {
-    constexpr bool kPilot = kMode == 1, kRefine = kMode == 2;
+    constexpr bool kPilot = kMode == 1, kRefine = kMode == 2, kBound = kMode == 3, kEmit = kMode == 4;
     extern __shared__ __align__(16) uint32_t kw_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = blockIdx.x * kKwWarps + warp;
@@ -863,6 +911,7 @@ kth_warp_kernel(KthParams p, int nq) {
                 if (!p.overflow[q]) atomicAdd(p.stats + 0, 1);
                 p.overflow[q] = 1;
                 if (kRefine) { p.cand_cnt[q] = 0; p.thr[q] = INFINITY; }      // collect nothing more for it
+                else if (kBound) { for (int i = 0; i < p.k; ++i) p.kth_bound[(int64_t)q * p.k + i] = -INFINITY; }   // this rank's exact scan answers; no bound from here
                 else p.fin_cnt[q] = 0;
             }
             return;
@@ -877,7 +926,7 @@ kth_warp_kernel(KthParams p, int nq) {
     bool lists_ok = false;      // lane lists hold every entry >= pivot
     uint32_t pivot = 0;
     int mine = 0;               // survivors in this lane's list
-    if (kk > 0) {
+    if (kk > 0 && !kEmit) {
         if (count > 32 * kKwSlots) {                 // pivot from 512 strided samples
             uint32_t sk[16];
             const int stride = count >> 9;
@@ -931,9 +980,41 @@ kth_warp_kernel(KthParams p, int nq) {
             }
         }
     }
+    if (kBound) {
+        // This rank's contribution to the global bound: lower bounds (score - eps) of the true cosines of its k best
+        // rows (any k distinct rows do; -inf pads a shorter list).  The lists are built by a later kEmit launch.
+        float *dst = p.kth_bound + (int64_t)q * p.k;
+        for (int i = lane; i < p.k; i += 32) dst[i] = -INFINITY;
+        __syncwarp();
+        int outb = 0;
+        auto put = [&](bool keep, float score) {
+            const unsigned mask = __ballot_sync(kFull, keep);
+            const int at = outb + __popc(mask & ((1u << lane) - 1u));
+            if (keep && at < p.k) dst[at] = __fsub_rd(score, eps);
+            outb += __popc(mask);
+        };
+        if (kk > 0) {
+            if (lists_ok) {
+                const int most = __reduce_max_sync(kFull, mine);
+                for (int j = 0; j < most && outb < p.k; ++j) {
+                    const bool have = j < mine;
+                    const uint32_t key = have ? lkey[j * 32 + lane] : 0u;
+                    put(have && key >= best, key_float(key));
+                }
+            } else {
+                for (int i0 = 0; i0 < count && outb < p.k; i0 += 32) {
+                    const int i = i0 + lane;
+                    const float v = i < count ? src[i] : 0.f;
+                    put(i < count && float_key(v) >= best, v);
+                }
+            }
+        }
+        return;
+    }
     // cannot prune while fewer than k scores have been seen
     float cut = -INFINITY;
-    if (kk >= p.k) cut = __fsub_rd(key_float(best), __fmul_ru(2.0f, eps));
+    if (kEmit) { const float b = p.kth_bound[q]; if (b > -INFINITY) cut = __fsub_rd(b, eps); }
+    else if (kk >= p.k) cut = __fsub_rd(key_float(best), __fmul_ru(2.0f, eps));
     const uint32_t cut_key = cut == -INFINITY ? 0u : float_key(cut);
     int out = 0;
     auto emit = [&](bool keep, float score, int idx) {
@@ -1035,12 +1116,14 @@ static int g_block_rows = 131072;  // rows scored between two refinements of the
 static int g_pilot_rows = kKthMax; // rows of the pilot block whose scores are dumped for the first thresholds (key 10)
 static int g_first_block = 0;      // rows up to the first refinement (key 11); 0 = g_block_rows
 static int g_rerank_ctas_per_sm = 0; // key 13: cap on resident re-rank CTAs per SM (0 = whatever fits)
-static int g_rerank_rows = 8;     // candidate rows per warp pass of the re-rank (2, 4 or 8)
+static int g_rerank_rows = 4;     // candidate rows per warp pass of the re-rank (2, 4, 8; 16 for the warp kernel)
 static int g_rerank_phase_mb = -1; // row range kept L2-resident per re-rank phase; 0 = never split; -1 = 64 MB for the warp kernel, unsplit otherwise
-static int g_rerank_kernel = 0;    // key 14: 0 = warp-granular items from a global queue, 1 = one CTA per query (shared-memory query)
+static int g_rerank_kernel = 1;    // key 14: 0 = warp-granular items from a global queue, 1 = one CTA per query (shared-memory query)
 static int g_rerank_ctas = 0;      // key 15: CTAs per SM of the warp kernel (0 = what fits)
 static int g_rerank_subs = 0;      // key 16: items per query of the unsplit warp re-rank (0 = 4)
-static int g_side_job = 1;         // key 17: 0 = ignore side jobs (the resume call then re-ranks everything)
+static int g_side_job = 0;         // key 17: 1 = side jobs on: helper warps in the GEMM kernel re-rank the previous batch (measured slower:
+                                   // the GEMM's TMA stream and the helpers' gathers queue behind each other)
+static int g_rerank_pipe = 1;      // key 18: CTA-per-query re-rank with software-pipelined row loads
 
 
 static int launch_knn_gemm(const CUtensorMap &tmap_q, const CUtensorMap &tmap_s, const GemmParams &gp, cudaStream_t s,
@@ -1107,6 +1190,7 @@ static BatchWs batch_ws_layout(int64_t n, int64_t nq, int64_t ld_h) {
 static int make_rerank_params(RerankParams &rp, bool &warp_kernel, const float *vectors, const double *pp, int64_t n,
                               int32_t dim, int64_t ld, int32_t id_base, const double *queries, int64_t nq, int64_t q_ld,
                               int32_t k, const uint8_t *overflow, void *workspace, size_t workspace_bytes);
+static bool side_jobs_enabled() { return g_gemm_pair && g_side_job; }
 
 }  // namespace morna
 
@@ -1140,7 +1224,8 @@ extern "C" size_t morna_knn_batched_workspace_bytes(int64_t n, int64_t nq, int32
 extern "C" int morna_knn_batched_score(const void *hs, int64_t ld_h, const float *rho_max, int64_t n, int32_t dim,
                                        int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
                                        uint8_t *overflow, int32_t *stats, void *workspace, size_t workspace_bytes,
-                                       void *const *phase_events, const morna_rerank_job *side_job, void *stream) {
+                                       void *const *phase_events, const morna_rerank_job *side_job, float *kth_bound,
+                                       void *stream) {
     if (!hs || !rho_max || !queries || !overflow || !stats || n <= 0 || n > kBatchedMaxRows || nq <= 0 || dim <= 0 ||
         q_ld < dim || k <= 0 || k > kFinCap / 2 || ld_h != morna_tensor_operand_ld(dim))
         return MORNA_ERR_INVALID_ARGUMENT;
@@ -1155,7 +1240,7 @@ extern "C" int morna_knn_batched_score(const void *hs, int64_t ld_h, const float
                                      side_job->ld, side_job->id_base, side_job->queries, side_job->nq, side_job->q_ld,
                                      side_job->k, side_job->overflow, side_job->workspace, side_job->workspace_bytes);
         if (rcj != MORNA_OK) return rcj;
-        if (warp_kernel && g_gemm_pair && g_side_job) side_ptr = &side;      // otherwise everything is left to the resume call
+        if (warp_kernel && side_jobs_enabled()) side_ptr = &side;            // otherwise everything is left to the resume call
     }
     cudaStream_t s = (cudaStream_t)stream;
     unsigned char *ws = (unsigned char *)workspace;
@@ -1241,9 +1326,78 @@ extern "C" int morna_knn_batched_score(const void *hs, int64_t ld_h, const float
         }
     }
     mark();                                                      // 4: filter GEMM(s)
-    kth_warp_kernel<0><<<kth_grid, kKwWarps * 32, kKwSmem, s>>>(kp, (int)nq);
+    if (kth_bound) {             // rows-sharded search: only this rank's bound; morna_knn_batched_finalize builds the lists
+        kp.kth_bound = kth_bound;
+        MORNA_CUDA_TRY(cudaFuncSetAttribute(kth_warp_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKwSmem));
+        kth_warp_kernel<3><<<kth_grid, kKwWarps * 32, kKwSmem, s>>>(kp, (int)nq);
+    } else {
+        kth_warp_kernel<0><<<kth_grid, kKwWarps * 32, kKwSmem, s>>>(kp, (int)nq);
+    }
     MORNA_LAUNCH_CHECK();
     mark();                                                      // 5: final candidate lists
+    return MORNA_OK;
+}
+
+namespace morna {
+// k-th largest of the n_lists * k lower bounds the ranks gathered for a query (one warp per query, bisection on the
+// monotone keys): at least k distinct rows over all shards have a true cosine >= the result.
+__global__ void __launch_bounds__(256)
+union_kth_kernel(const float *__restrict__ vals, int32_t n_lists, int64_t nq, int32_t k, float *__restrict__ bound) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const int total = n_lists * k;
+    uint32_t best = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t trial = best | (1u << bit);
+        int c = 0;
+        for (int e = lane; e < total; e += 32) {
+            const int g = e / k, j = e - g * k;
+            c += float_key(vals[((int64_t)g * nq + q) * k + j]) >= trial;
+        }
+        c = __reduce_add_sync(kFull, c);
+        if (c >= k) best = trial;
+    }
+    if (lane == 0) bound[q] = best ? key_float(best) : -INFINITY;     // fewer than k values in all: no bound
+}
+}  // namespace morna
+
+extern "C" int morna_union_kth_bound(const float *vals, int32_t n_lists, int64_t nq, int32_t k, float *bound, void *stream) {
+    if (!vals || !bound || n_lists <= 0 || nq < 0 || k <= 0) return MORNA_ERR_INVALID_ARGUMENT;
+    if (nq == 0) return MORNA_OK;
+    morna::union_kth_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, (cudaStream_t)stream>>>(vals, n_lists, nq, k, bound);
+    MORNA_LAUNCH_CHECK();
+    return MORNA_OK;
+}
+
+// Rows-sharded search, second half of the scoring: every query's final candidate list from a bound on the k-th best
+// cosine that holds over ALL shards -- the caller all-reduces (MAX) the kth_bound arrays the ranks' scoring calls wrote.
+// A row of the global top-k has true cosine >= that bound, hence a score >= bound - eps of this rank.
+extern "C" int morna_knn_batched_finalize(int64_t n, int64_t nq, int32_t dim, int32_t k, const float *kth_bound,
+                                          uint8_t *overflow, int32_t *stats, void *workspace, size_t workspace_bytes,
+                                          void *stream) {
+    if (!kth_bound || !overflow || !stats || n <= 0 || n > kBatchedMaxRows || nq <= 0 || dim <= 0 || k <= 0 || k > kFinCap / 2)
+        return MORNA_ERR_INVALID_ARGUMENT;
+    BatchWs w = batch_ws_layout(n, nq, morna_tensor_operand_ld(dim));
+    if (!workspace || workspace_bytes < w.total) return MORNA_ERR_WORKSPACE_TOO_SMALL;
+    unsigned char *ws = (unsigned char *)workspace;
+    // which of the two list buffers is current: one swap per refinement between row blocks (same walk as the scoring call)
+    int swaps = 0;
+    for (int64_t b0 = w.n0; b0 < n;) {
+        int64_t b1 = b0 == w.n0 ? (int64_t)(g_first_block > 0 ? g_first_block : g_block_rows) : b0 + g_block_rows;
+        if (b1 > n || b1 <= b0) b1 = n;
+        b0 = b1;
+        if (b0 < n) ++swaps;
+    }
+    KthParams kp{};
+    kp.k = k; kp.n0 = (int32_t)w.n0; kp.cap = kCandCap; kp.fcap = kFinCap; kp.eps = (const float *)(ws + w.eps);
+    kp.cand_score = (float *)(ws + ((swaps & 1) ? w.cand2_score : w.cand_score));
+    kp.cand_id = (int32_t *)(ws + ((swaps & 1) ? w.cand2_id : w.cand_id));
+    kp.cand_cnt = (int32_t *)(ws + w.cand_cnt); kp.fin_id = (int32_t *)(ws + w.fin_id); kp.fin_cnt = (int32_t *)(ws + w.fin_cnt);
+    kp.overflow = overflow; kp.stats = stats; kp.kth_bound = const_cast<float *>(kth_bound);
+    MORNA_CUDA_TRY(cudaFuncSetAttribute(kth_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKwSmem));
+    kth_warp_kernel<4><<<(unsigned)((nq + kKwWarps - 1) / kKwWarps), kKwWarps * 32, kKwSmem, (cudaStream_t)stream>>>(kp, (int)nq);
+    MORNA_LAUNCH_CHECK();
     return MORNA_OK;
 }
 
@@ -1301,10 +1455,11 @@ extern "C" int morna_knn_batched_rerank(const float *vectors, const double *pp, 
                                 workspace_bytes);
     if (rc != MORNA_OK) return rc;
     cudaStream_t s = (cudaStream_t)stream;
+    if (resume && !(warp_kernel && side_jobs_enabled())) resume = 0;        // no helper warps ran: the whole batch is still to do
     if (warp_kernel) {
         // warp-granular items (any dim: the query is read from global memory)
         if (!resume) MORNA_CUDA_TRY(cudaMemsetAsync(rp.queue, 0, sizeof(unsigned long long), s));
-        auto kern = g_rerank_rows == 16 ? rerank_warp_kernel<16, 1> : g_rerank_rows == 4 ? rerank_warp_kernel<4, 4>
+        auto kern = g_rerank_rows == 16 ? rerank_warp_kernel<16, 1> : g_rerank_rows == 2 ? rerank_warp_kernel<4, 4>
                                                                                        : rerank_warp_kernel<8, 2>;
         const size_t smem = (size_t)kRwWarps * kFinCap * sizeof(int);
         // shared-memory carve-out at its maximum, so that CTAs of this kernel and the GEMM (130 KB) can share an SM
@@ -1319,9 +1474,10 @@ extern "C" int morna_knn_batched_rerank(const float *vectors, const double *pp, 
         kern<<<(unsigned)grid, kRwWarps * 32, smem, s>>>(rp);
         MORNA_LAUNCH_CHECK();
     } else {
-        if (resume) return MORNA_ERR_INVALID_ARGUMENT;
         const size_t rr_smem = (size_t)ld * sizeof(double) + (size_t)kFinCap * sizeof(int);
         auto kern = g_rerank_rows == 2 ? rerank_dist_kernel<2> : g_rerank_rows == 4 ? rerank_dist_kernel<4> : rerank_dist_kernel<8>;
+        if (g_rerank_pipe) kern = g_rerank_rows == 4 ? rerank_dist_kernel<4, true> : g_rerank_rows == 16 ? rerank_dist_kernel<16, true>
+                                                                                                        : rerank_dist_kernel<8, true>;
         MORNA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
         int per_sm = 0;
         MORNA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRrThreads, rr_smem));
@@ -1347,7 +1503,7 @@ extern "C" int morna_knn_batched(const float *vectors, const double *pp, const v
                                  size_t workspace_bytes, void *const *phase_events, void *stream) {
     if (!vectors || !pp || !out_ids || !out_dist || ld < dim || (ld & 3)) return MORNA_ERR_INVALID_ARGUMENT;
     int rc = morna_knn_batched_score(hs, ld_h, rho_max, n, dim, id_base, queries, nq, q_ld, k, overflow, stats,
-                                     workspace, workspace_bytes, phase_events, nullptr, stream);
+                                     workspace, workspace_bytes, phase_events, nullptr, nullptr, stream);
     if (rc != MORNA_OK) return rc;
     rc = morna_knn_batched_rerank(vectors, pp, n, dim, ld, id_base, queries, nq, q_ld, k, out_ids, out_dist, overflow,
                                   workspace, workspace_bytes, 0, stream);
@@ -1409,6 +1565,7 @@ extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
     else if (key == 15) g_rerank_ctas = value;
     else if (key == 16) g_rerank_subs = value;
     else if (key == 17) g_side_job = value;
+    else if (key == 18) g_rerank_pipe = value;
 
     else return MORNA_ERR_INVALID_ARGUMENT;
     return MORNA_OK;

@@ -98,3 +98,45 @@ def sharded_exact_search(local_search, queries, k, group=None, merge=None):
         return merge_sorted_lists(gi, gd, k)
     ids, dists = all_gather_topk(ids, dists, group)
     return (merge or merge_topk)(ids, dists, k)
+
+
+def sharded_batched_search(search, queries, k, group=None, check_overflow=True):
+    """Rows-sharded exact search of a query batch on the tensor-core path, one process per GPU.  `search` holds this
+    rank's row block (MornaSearch(..., shard=(rank, world))), `queries` (CUDA float64 [nq x dim]) are replicated.
+
+      1. every rank scores the queries against its rows and writes, per query, lower bounds of the true cosines of
+         its k best rows (fp16 score minus the rank's rigorous error bound);
+      2. ONE all-gather (4 * nq * k bytes per rank) and a k-th-largest over the world * k values per query give a bound
+         that at least k rows over ALL shards reach -- so the ranks together re-rank about k rows per query instead of
+         k rows each;
+      3. every rank re-ranks (exact FP64) and orders its surviving rows; ONE more all-gather moves the [nq x k] lists
+         (ids and distances packed in one buffer) and every rank merges them by rank counting.
+
+    Returns (ids, dists), identical on every rank and identical to one process scanning all rows."""
+    import torch.distributed as td
+    world = td.get_world_size(group) if (td.is_available() and td.is_initialized()) else 1
+    if world == 1:
+        return search.batched_search_device(queries, k, check_overflow=check_overflow)
+    vals = search.batched_score_bound(queries, k)
+    every = torch.empty((world,) + tuple(vals.shape), dtype=vals.dtype, device=vals.device)
+    td.all_gather_into_tensor(every, vals, group=group)
+    bound = search.union_kth_bound(every, k)
+    ids, dists = search.batched_finish_bound(bound, check_overflow=check_overflow)
+    return gather_merge_packed(ids, dists, k, group)
+
+
+def gather_merge_packed(ids, dists, k, group=None):
+    """All-gather of every rank's sorted [nq x k] lists in ONE collective (distances and ids packed into one byte
+    buffer per rank), then the rank-counting merge."""
+    import torch.distributed as td
+    world = td.get_world_size(group)
+    nq, k_in = ids.shape
+    nd, ni = nq * k_in * 8, nq * k_in * 4
+    mine = torch.empty(nd + ni, dtype=torch.uint8, device=ids.device)
+    mine[:nd].view(torch.float64).copy_(dists.reshape(-1))
+    mine[nd:].view(torch.int32).copy_(ids.reshape(-1))
+    every = torch.empty((world, nd + ni), dtype=torch.uint8, device=ids.device)
+    td.all_gather_into_tensor(every, mine, group=group)
+    gd = every[:, :nd].contiguous().view(torch.float64).view(world, nq, k_in)
+    gi = every[:, nd:].contiguous().view(torch.int32).view(world, nq, k_in)
+    return merge_sorted_lists(gi, gd, k)

@@ -315,7 +315,75 @@ class MornaSearch(object):
             return parts[0][2], parts[0][3]
         return mdist.merge_topk(torch.cat([p[2] for p in parts], 1), torch.cat([p[3] for p in parts], 1), k, stream)
 
-    def search_batches(self, batches, k, depth=2):
+    # rows-sharded search: scoring up to this rank's bound on the k-th best cosine, then -- once the caller has
+    # all-reduced the bounds -- final lists, re-rank and order (see dist.sharded_batched_search)
+    def batched_score_bound(self, queries, k):
+        """First half on this rank's rows: returns float32 [nq x k] lower bounds of the true cosines of its k best
+        rows per query (-inf: nothing from this rank).  The candidate state stays in this object until
+        batched_finish_bound."""
+        self.enable_tensor_path()
+        assert queries.is_cuda and queries.dtype == torch.float64 and queries.dim() == 2 and queries.shape[1] == self.dim
+        queries = queries.contiguous()
+        nq, dev = queries.shape[0], self.device
+        n = self.row_hi - self.row_lo
+        bound = torch.full((nq, max(k, 1)), float("-inf"), dtype=torch.float32, device=dev)
+        tensor = 0 < k <= min(n, 512) and n <= self.BATCH_BLOCK_ROWS and nq > 0
+        self._bound_state = (queries, k, tensor, None)
+        if not tensor:
+            return bound                     # tiny shard or huge k: the exact scan answers locally, nothing to prune with
+        with torch.cuda.device(dev):
+            overflow = torch.empty(nq, dtype=torch.uint8, device=dev)
+            stats = torch.empty(4, dtype=torch.int32, device=dev)
+            need = self.lib.morna_knn_batched_workspace_bytes(n, nq, self.dim, k)
+            sid = torch.cuda.current_stream(dev).cuda_stream
+            ws = self._bws.get(sid)
+            if ws is None or ws.numel() < need:
+                ws = self._bws[sid] = _lib.workspace(need, dev)
+            _lib.check(self.lib.morna_knn_batched_score(
+                _lib.dev_ptr(self.hs), self.ld_h, _lib.dev_ptr(self.rho_max), n, self.dim, self.row_lo, _lib.ptr(queries), nq,
+                self.dim, k, _lib.dev_ptr(overflow), _lib.dev_ptr(stats), _lib.dev_ptr(ws), ws.numel(), None, None,
+                _lib.dev_ptr(bound), _lib.stream_ptr()), "morna_knn_batched_score")
+        self._bound_state = (queries, k, tensor, (overflow, stats, ws))
+        return bound
+
+    def union_kth_bound(self, gathered, k):
+        """gathered: float32 [lists x nq x k] (the all-gathered batched_score_bound results) -> float32 [nq], per query a
+        value that at least k rows over all shards reach or exceed in true cosine."""
+        lists, nq = gathered.shape[0], gathered.shape[1]
+        out = torch.empty(nq, dtype=torch.float32, device=gathered.device)
+        gathered = gathered.contiguous()
+        with torch.cuda.device(gathered.device):
+            _lib.check(self.lib.morna_union_kth_bound(_lib.dev_ptr(gathered), lists, nq, k, _lib.dev_ptr(out), _lib.stream_ptr()),
+                       "morna_union_kth_bound")
+        return out
+
+    def batched_finish_bound(self, bound, check_overflow=True):
+        """Second half: `bound` float32 [nq] = union_kth_bound of every rank's batched_score_bound result.  Returns this
+        rank's (ids, dists), sorted under the reference order with GLOBAL ids; together the ranks' lists hold the global
+        top-k (each rank re-ranks only its rows whose score can still reach the global k-th place)."""
+        queries, k, tensor, st = self._bound_state
+        self._bound_state = None
+        if not tensor:
+            return self.exact_search_device(queries, k, allow_single=False)
+        overflow, stats, ws = st
+        nq, dev = queries.shape[0], self.device
+        n = self.row_hi - self.row_lo
+        out_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+        out_d = torch.empty((nq, k), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.morna_knn_batched_finalize(n, nq, self.dim, k, _lib.dev_ptr(bound), _lib.dev_ptr(overflow),
+                                                           _lib.dev_ptr(stats), _lib.dev_ptr(ws), ws.numel(), _lib.stream_ptr()),
+                       "morna_knn_batched_finalize")
+            _lib.check(self.lib.morna_knn_batched_rerank(
+                _lib.dev_ptr(self.vectors), _lib.dev_ptr(self.pp), n, self.dim, self.ld, self.row_lo, _lib.ptr(queries), nq,
+                self.dim, k, _lib.dev_ptr(out_ids), _lib.dev_ptr(out_d), _lib.dev_ptr(overflow), _lib.dev_ptr(ws), ws.numel(), 0,
+                _lib.stream_ptr()), "morna_knn_batched_rerank")
+        parts = [(0, n, out_ids, out_d, overflow, stats)]
+        if check_overflow:
+            return self._batched_finish(parts, queries, k)
+        return out_ids, out_d
+
+    def search_batches(self, batches, k, depth=2, side_job=False):
         """Streams query batches through the GPU: generator over ``batches`` (each a numpy
         [nq x dim] float32/float64 array) yielding ``(ids, dists)`` numpy arrays in order -- the same
         results as ``exact_search_batch`` per batch.  ``depth`` batches are in flight, each on its own
@@ -323,8 +391,8 @@ class MornaSearch(object):
         copy and batch i-1's device->host copy overlap batch i's kernels."""
         pipes = self.__dict__.setdefault("_pipes", {})
         pipe = pipes.get((k, depth))           # slots (streams, pinned buffers, workspaces) are kept between calls
-        if pipe is None or pipe.head != pipe.tail:
-            pipe = pipes[(k, depth)] = BatchPipeline(self, k, depth)
+        if pipe is None or pipe.head != pipe.tail or pipe.side_job != (bool(side_job) and depth > 1):
+            pipe = pipes[(k, depth)] = BatchPipeline(self, k, depth, side_job)
         pending = 0
         for q in batches:
             if pending == depth:
@@ -413,8 +481,9 @@ class BatchPipeline(object):
     collect() if nothing followed.  submit() returns at once; collect() waits for the oldest batch and returns
     host arrays (views of the slot's pinned buffers, valid until the slot is reused ``depth`` submits later)."""
 
-    def __init__(self, search, k, depth=2):
+    def __init__(self, search, k, depth=2, side_job=False):
         self.search, self.k, self.depth = search, k, depth
+        self.side_job = bool(side_job) and depth > 1
         search.enable_tensor_path()
         dev = search.device
         self.compute = torch.cuda.Stream(device=dev)
@@ -422,6 +491,9 @@ class BatchPipeline(object):
         for _ in range(depth):
             sl = _PipeSlot()
             sl.stream = torch.cuda.Stream(device=dev)        # this slot's copies
+            # kernels: one shared stream when a batch's re-rank rides in the next batch's scoring call, else a stream per
+            # slot (consecutive batches then overlap a little at their edges)
+            sl.compute = self.compute if self.side_job else torch.cuda.Stream(device=dev)
             sl.h2d, sl.scored, sl.ranked, sl.done = (torch.cuda.Event() for _ in range(4))
             sl.nq = -1
             sl.host_q = sl.ws = sl.job = sl.parts = None
@@ -455,7 +527,7 @@ class BatchPipeline(object):
         job = ctypes.byref(side.job) if side is not None else None
         _lib.check(lib.morna_knn_batched_score(
             _lib.dev_ptr(s.hs), s.ld_h, _lib.dev_ptr(s.rho_max), n, s.dim, s.row_lo, _lib.ptr(sl.qd), sl.nq, s.dim, k,
-            _lib.dev_ptr(sl.overflow), _lib.dev_ptr(sl.stats), _lib.dev_ptr(sl.ws), sl.ws.numel(), None, job,
+            _lib.dev_ptr(sl.overflow), _lib.dev_ptr(sl.stats), _lib.dev_ptr(sl.ws), sl.ws.numel(), None, job, None,
             _lib.stream_ptr()), "morna_knn_batched_score")
         sl.job = _lib.RerankJob(s.vectors.data_ptr(), s.pp.data_ptr(), n, s.dim, s.ld, s.row_lo, sl.qd.data_ptr(), sl.nq, s.dim, k,
                                 sl.overflow.data_ptr(), sl.ws.data_ptr(), sl.ws.numel())
@@ -504,8 +576,8 @@ class BatchPipeline(object):
             sl.qd = src.to(s.device, non_blocking=True).to(torch.float64).contiguous()   # float32 widens exactly
             sl.h2d.record(sl.stream)
         n = s.row_hi - s.row_lo
-        self.compute.wait_event(sl.h2d)
-        with torch.cuda.stream(self.compute):
+        sl.compute.wait_event(sl.h2d)
+        with torch.cuda.stream(sl.compute):
             prev, self.unranked = self.unranked, None
             sl.parts = sl.job = None
             sl.mode = "plain"
@@ -523,11 +595,15 @@ class BatchPipeline(object):
                 sl.parts = s._batched_launch(sl.qd, k)
                 sl.ranked.record()
                 self._copy_back(sl, None, None, [part[5] for part in sl.parts])
-            else:
+            elif not self.side_job:
                 sl.mode = "pipelined"
-                self._score(sl, prev if (prev is not None and self.depth > 1) else None)
+                self._score(sl, None)
+                self._rerank(sl, resume=False)
+            else:                            # the previous batch's re-rank rides in this batch's GEMM kernels
+                sl.mode = "pipelined"
+                self._score(sl, prev)
                 if prev is not None:
-                    self._rerank(prev, resume=self.depth > 1)
+                    self._rerank(prev, resume=True)
                 self.unranked = sl
 
     def collect(self):
@@ -537,7 +613,7 @@ class BatchPipeline(object):
         self.tail += 1
         if self.unranked is sl:              # nothing was submitted after it: its re-rank runs on its own
             self.unranked = None
-            with torch.cuda.stream(self.compute):
+            with torch.cuda.stream(sl.compute):
                 self._rerank(sl, resume=False)
         sl.done.synchronize()
         if sl.mode == "plain":
@@ -547,11 +623,11 @@ class BatchPipeline(object):
         nparts = len(sl.parts)
         overflowed = int(sl.host_stats[:nparts, 0].sum()) > 0
         if overflowed or nparts > 1:         # rare: exact-scan fix-up and/or merge of row blocks, then copy again
-            with torch.cuda.stream(self.compute):
+            with torch.cuda.stream(sl.compute):
                 ids, d = s._batched_finish(sl.parts, sl.qd, k, host_stats=[sl.host_stats[i] for i in range(nparts)])
                 sl.host_ids.copy_(ids, non_blocking=True)
                 sl.host_d.copy_(d, non_blocking=True)
-            self.compute.synchronize()
+            sl.compute.synchronize()
         else:
             s.last_stats = sl.host_stats[0].to(torch.int64).tolist()
         return sl.host_ids.numpy(), sl.host_d.numpy()

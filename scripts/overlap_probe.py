@@ -43,7 +43,7 @@ class Slot:
 slots = [Slot(), Slot()]
 def score(sl, stream):
     _lib.check(lib.morna_knn_batched_score(_lib.dev_ptr(s.hs), s.ld_h, _lib.dev_ptr(s.rho_max), N, D, 0, _lib.dev_ptr(q), Q, D, K,
-               _lib.dev_ptr(sl.ov), _lib.dev_ptr(sl.st), _lib.dev_ptr(sl.ws), sl.ws.numel(), None, None, _lib.stream_ptr(stream)), "score")
+               _lib.dev_ptr(sl.ov), _lib.dev_ptr(sl.st), _lib.dev_ptr(sl.ws), sl.ws.numel(), None, None, None, _lib.stream_ptr(stream)), "score")
 def rerank(sl, stream):
     _lib.check(lib.morna_knn_batched_rerank(_lib.dev_ptr(s.vectors), _lib.dev_ptr(s.pp), N, D, s.ld, 0, _lib.dev_ptr(q), Q, D, K,
                _lib.dev_ptr(sl.ids), _lib.dev_ptr(sl.d), _lib.dev_ptr(sl.ov), _lib.dev_ptr(sl.ws), sl.ws.numel(), 0, _lib.stream_ptr(stream)), "rerank")

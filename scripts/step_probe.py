@@ -52,7 +52,7 @@ ws = _lib.workspace(need, "cuda"); ov = torch.zeros(Q, dtype=torch.uint8, device
 oi = torch.empty((Q, K), dtype=torch.int32, device="cuda"); od = torch.empty((Q, K), dtype=torch.float64, device="cuda")
 def score():
     _lib.check(lib.morna_knn_batched_score(_lib.dev_ptr(s.hs), s.ld_h, _lib.dev_ptr(s.rho_max), N, D, 0, _lib.dev_ptr(q), Q, D, K,
-               _lib.dev_ptr(ov), _lib.dev_ptr(st), _lib.dev_ptr(ws), ws.numel(), None, None, _lib.stream_ptr()), "score")
+               _lib.dev_ptr(ov), _lib.dev_ptr(st), _lib.dev_ptr(ws), ws.numel(), None, None, None, _lib.stream_ptr()), "score")
 def rerank():
     _lib.check(lib.morna_knn_batched_rerank(_lib.dev_ptr(s.vectors), _lib.dev_ptr(s.pp), N, D, s.ld, 0, _lib.dev_ptr(q), Q, D, K,
                _lib.dev_ptr(oi), _lib.dev_ptr(od), _lib.dev_ptr(ov), _lib.dev_ptr(ws), ws.numel(), 0, _lib.stream_ptr()), "rerank")
@@ -71,7 +71,7 @@ lib.morna_debug_set_tuning(14, 0); lib.morna_debug_set_tuning(5, 8); lib.morna_d
 # ---- the streaming pipeline, resident queries
 def pipeline(nb=20):
     last = None
-    for ids_, d_ in s.search_batches((q for _ in range(nb)), K, depth=2):
+    for ids_, d_ in s.search_batches((q for _ in range(nb)), K, depth=2, side_job=True):
         last = (ids_, d_)
     return last
 for side in (1, 0):
@@ -82,7 +82,7 @@ for side in (1, 0):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); last = pipeline(20)
         pipe = s._pipes[(K, 2)]
-        torch.cuda.current_stream().wait_stream(pipe.compute)
+        torch.cuda.current_stream().wait_stream(pipe.compute); [torch.cuda.current_stream().wait_stream(sl_.compute) for sl_ in pipe.slots]
         e1.record(); torch.cuda.synchronize()
         ids_h, d_h = last
         ok = torch.equal(torch.from_numpy(ids_h).cuda()[pick], ref_ids) and torch.equal(torch.from_numpy(d_h).cuda()[pick], ref_d)

@@ -144,13 +144,17 @@ def test_batched_row_blocks_merge():
     assert torch.equal(b_ids, e_ids) and torch.equal(b_d, e_d)
 
 
-@pytest.mark.parametrize("rows_per_warp,phase_mb", [(2, 0), (4, 1), (8, 0), (8, 1), (4, 0)])
-def test_rerank_variants_agree(rows_per_warp, phase_mb):
-    """Rows per warp pass and the L2 phase split only change the schedule of the re-rank, never a bit."""
+@pytest.mark.parametrize("kernel,pipe,rows_per_warp,phase_mb", [(1, 0, 2, 0), (1, 0, 4, 1), (1, 0, 8, 0), (1, 1, 8, 1), (1, 1, 4, 0),
+                                                                (1, 1, 16, 0), (0, 0, 8, 0), (0, 0, 16, 1), (0, 0, 2, 1)])
+def test_rerank_variants_agree(kernel, pipe, rows_per_warp, phase_mb):
+    """Which kernel re-ranks (CTA per query with the query in shared memory, plain or software-pipelined; warp-granular
+    queue items with the query read from global memory), rows per warp pass and the L2 phase split only change the
+    schedule of the re-rank, never a bit."""
     from morna_b200 import _lib
     lib = _lib.load()
     try:
-        assert lib.morna_debug_set_tuning(5, rows_per_warp) == 0 and lib.morna_debug_set_tuning(6, phase_mb) == 0
+        for key, val in ((14, kernel), (18, pipe), (5, rows_per_warp), (6, phase_mb)):
+            assert lib.morna_debug_set_tuning(key, val) == 0
         rng = np.random.default_rng(123)
         n, d, nq, k = 4100, 300, 600, 50          # every row is re-ranked ~9 times: the phase split engages
         S = rng.standard_normal((n, d)).astype(np.float32)
@@ -166,8 +170,35 @@ def test_rerank_variants_agree(rows_per_warp, phase_mb):
         b_ids, b_d = srch.batched_search_device(q, k)
         assert torch.equal(b_ids, e_ids) and torch.equal(b_d, e_d)
     finally:
-        lib.morna_debug_set_tuning(5, 8)
-        lib.morna_debug_set_tuning(6, 0)
+        for key, val in ((14, 1), (18, 1), (5, 4), (6, -1)):
+            lib.morna_debug_set_tuning(key, val)
+
+
+@pytest.mark.parametrize("side", [1, 0])
+def test_side_job_pipeline_equals_the_synchronous_call(side):
+    """The scoring call of batch i+1 carrying batch i's re-rank as its side job (helper warps inside the GEMM kernel,
+    then the resume call) returns the same lists as the plain call -- with the side job on (key 17) and ignored."""
+    from morna_b200 import _lib
+    lib = _lib.load()
+    try:
+        assert lib.morna_debug_set_tuning(17, side) == 0 and lib.morna_debug_set_tuning(14, 0 if side else 1) == 0
+        rng = np.random.default_rng(17)
+        n, d, k = 9000, 520, 30
+        S = rng.standard_normal((n, d)).astype(np.float32)
+        S[20:23] = S[19]
+        srch = make_search(S)
+        batches = []
+        for nq in (700, 700, 333, 700, 64):
+            Q = S[rng.permutation(n)[:nq]] + np.float32(0.03) * rng.standard_normal((nq, d)).astype(np.float32)
+            Q[0] = S[19]
+            batches.append(Q)
+        want = [srch.exact_search_batch(B, k, tensor_cores=False) for B in batches]
+        got = [(i.copy(), d_.copy()) for i, d_ in srch.search_batches(iter(batches), k, depth=2, side_job=True)]
+        for (gi, gd), (wi, wd) in zip(got, want):
+            assert np.array_equal(gi, wi) and np.array_equal(gd, wd)
+    finally:
+        lib.morna_debug_set_tuning(17, 0)
+        lib.morna_debug_set_tuning(14, 1)
 
 
 def test_queries_too_large_for_the_scaled_rerank_go_to_the_exact_scan():

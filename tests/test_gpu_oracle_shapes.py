@@ -114,6 +114,39 @@ def test_two_row_shards_merged_equal_oracle_at_100k_rows():
     assert_lists_equal_oracle(S_host, Q_host, ids.cpu().numpy()[pick], dist.cpu().numpy()[pick], k, "two shards")
 
 
+@pytest.mark.parametrize("world", [2, 5])
+def test_sharded_bound_path_equals_unsharded_and_oracle(world):
+    """The rows-sharded search with its two exchange steps emulated in one process: every shard scores up to the lower
+    bounds of its k best cosines, the k-th largest of all shards' bounds is taken per query (what follows the
+    all-gather), every shard builds its lists from that global bound and re-ranks, the sorted lists are merged.  Together the shards re-rank about k rows per query --
+    not k per shard -- and the result is the unsharded one and the oracle's."""
+    from morna_b200 import dist as mdist
+    n, d, nq, k = 60000, 1000, 512, 100
+    S = synth.gauss(n, d, "cuda", seed=3)
+    S[1000:1004] = S[999]                         # ties inside a shard ...
+    S[n - 5] = S[999]                             # ... and across shards
+    q_in, _ = synth.queries(S, nq // 2)
+    q_out, _ = synth.queries(S, nq // 2, noise=0.05)
+    q = torch.cat([q_in, q_out]).contiguous()
+    q[0] = S[999].double()
+    whole = make_search(S)
+    w_ids, w_d = whole.batched_search_device(q, k)
+    shards = [make_search(S, shard=(r, world)) for r in range(world)]
+    vals = torch.stack([sh.batched_score_bound(q, k) for sh in shards])          # what the all-gather leaves
+    bound = shards[0].union_kth_bound(vals, k)
+    want = vals.permute(1, 0, 2).reshape(nq, -1).sort(dim=1, descending=True).values[:, k - 1]
+    assert torch.equal(bound, want) and bool((bound > -1).all())
+    parts = [sh.batched_finish_bound(bound.clone()) for sh in shards]
+    reranked = sum(sh.last_stats[2] for sh in shards) / nq
+    assert reranked < 1.6 * k, "the shards together re-ranked %.0f rows per query" % reranked
+    ids, dist = mdist.merge_sorted_lists(torch.stack([p_[0] for p_ in parts]), torch.stack([p_[1] for p_ in parts]), k)
+    assert torch.equal(ids, w_ids) and torch.equal(dist, w_d)
+    pick = np.arange(0, nq, 32)
+    assert_lists_equal_oracle(S.cpu().numpy(), q.cpu().numpy()[pick], ids.cpu().numpy()[pick], dist.cpu().numpy()[pick], k,
+                              "sharded bound")
+    print("rows re-ranked per query over %d shards: %.1f" % (world, reranked))
+
+
 def test_same_sign_rows_wide_features_stay_within_eps_and_equal_oracle():
     """Adversarial case for the fp32 accumulation term of eps: D = 10,000, every entry positive, so all partial sums
     of a dot product have one sign and grow to ~1 -- each of the D/16 chained tensor-core additions truncates at the
