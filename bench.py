@@ -233,6 +233,13 @@ def main():
             td.barrier()
         torch.cuda.synchronize()
 
+    t_start = time.perf_counter()
+
+    def note(what):
+        if rank == 0:
+            sys.stderr.write("[bench %6.1f s] %s\n" % (time.perf_counter() - t_start, what))
+            sys.stderr.flush()
+
     def max_over_ranks(x):
         t = torch.tensor([x], dtype=torch.float64, device=device)
         if world > 1:
@@ -247,6 +254,7 @@ def main():
     host_q = queries64.to(torch.float32).cpu().pin_memory()          # the queries are float32-valued rows
     srch.enable_tensor_path()
 
+    note("index resident")
     sampler = ClockSampler(local_rank); sampler.start()
     for _ in range(args.warmup):
         ids, d = srch.batched_search_device(queries64, K)
@@ -269,6 +277,7 @@ def main():
     ms_step = max_over_ranks(ms_step)
     value = nq * world / (ms_step / 1e3)
 
+    note("headline timed: %.3f ms per step" % ms_step)
     # ---- end to end through the host API: pinned host queries in, host results out, copies inside the timed region
     pipeline_ms(torch, srch, [host_q] * 3, K)
     barrier()
@@ -285,22 +294,26 @@ def main():
     roofline["step_frac_of_sustained"] = step_flops / (ms_step / 1e3) / 1e12 / peaks["bf16_tflops_sustained"]
     roofline["step_algorithmic"] = "2*Q*N*D flops / ms_per_step (prep, thresholds, top-k and re-rank included), Q=%d N=%d D=%d" % (nq, n_samples, DIM)
 
+    note("end to end and phases timed")
     extras = {}
     full = not args.only_headline and n_samples == N_SAMPLES and nq == N_QUERIES
     if full:
         extras["datasets"] = dataset_lines(torch, synth, MornaSearch, device, rank, max_over_ranks, world)
+    note("datasets done")
     del srch
     torch.cuda.empty_cache()
     if full and args.sharded_rows > 0:
         extras["rows_sharded"] = rows_sharded_line(torch, td, synth, MornaSearch, device, rank, world, args.sharded_rows,
                                                    max(5, min(args.steps, 10)), barrier, max_over_ranks)
         torch.cuda.empty_cache()
+    note("rows-sharded done")
     single = index = None
     if rank == 0 and full:
         single = single_query_line(torch, lib, _lib, synth, device, peaks)
         if args.index_pairs > 0:
             torch.cuda.empty_cache()
             index = index_build_line(torch, lib, _lib, device, peaks, args.index_pairs)
+    note("single query and index build done")
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
@@ -338,7 +351,7 @@ def dataset_lines(torch, synth, MornaSearch, device, rank, max_over_ranks, world
     """The headline step on the other SURVEY 8(d) inputs: clustered rows with in- and out-of-index queries, and
     intropolis-like sparse rows where thousands of rows tie (what the reference's own fixture looks like)."""
     out = {}
-    for kind, noise in (("tissue", 0.0), ("tissue", 0.05), ("gauss", 0.05), ("sparse", 0.0)):
+    for kind, noise in (("tissue", 0.0), ("tissue", 0.05), ("gauss", 0.05), ("sparse", 0.0), ("sparse_fixture", 0.0)):
         S = synth.matrix(kind, N_SAMPLES, DIM, device)
         srch = MornaSearch(vectors=S, stats=(N_SAMPLES, N_SAMPLES, DIM), device=device)
         q, _rows = synth.queries(S, N_QUERIES, seed=99 + rank, noise=noise)
@@ -348,8 +361,13 @@ def dataset_lines(torch, synth, MornaSearch, device, rank, max_over_ranks, world
         ms, _ = pipeline_ms(torch, srch, [q] * steps, K)
         ms = max_over_ranks(ms)
         name = kind + ("_out_of_index" if noise else "_in_index")
-        out[name] = {"queries_per_s": N_QUERIES * world / (ms / 1e3), "ms_per_step": ms,
-                     "overflowed_queries": int(srch.last_stats[0]), "reranked_per_query": srch.last_stats[2] / N_QUERIES}
+        if srch.csr is not None:
+            out[name] = {"queries_per_s": N_QUERIES * world / (ms / 1e3), "ms_per_step": ms,
+                         "path": "sparse index: CSR exact distances + exact selection (morna_knn_exact_sparse), no tensor pass",
+                         "nnz_per_row": float(srch.csr[1].numel()) / N_SAMPLES}
+        else:
+            out[name] = {"queries_per_s": N_QUERIES * world / (ms / 1e3), "ms_per_step": ms, "path": "tensor cores + FP64 re-rank",
+                         "overflowed_queries": int(srch.last_stats[0]), "reranked_per_query": srch.last_stats[2] / N_QUERIES}
         del srch, q
         torch.cuda.empty_cache()
     return out

@@ -198,6 +198,18 @@ int morna_knn_single(const float *vectors, const double *pp, int64_t n, int32_t 
                      int32_t id_base, const double *query, int32_t k, int32_t *out_ids, double *out_dist,
                      int32_t *fallback, void *workspace, size_t workspace_bytes, void *stream);
 
+/* exact_search_nn over a SPARSE index (rows with at most morna_sparse_max_nnz() non-zero buckets, e.g. an index built
+ * from a handful of junctions such as the reference's tests/tiny_intropolis.tsv, where thousands of rows are parallel
+ * and tie): the rows are given in CSR form and a (query, row) distance costs nnz(row) multiply-adds.  The non-zero
+ * terms are added in the dense kernels' order, so ids and distances are bit-identical to morna_knn_exact.
+ *   row_off [dev] int64[n+1]   cols [dev] int32[nnz] ascending within a row   vals [dev] float32[nnz] (non-zero)
+ *   pp      [dev] double[n] squared row norms (morna_row_norms of the dense rows) */
+int32_t morna_sparse_max_nnz(void);
+size_t morna_knn_exact_sparse_workspace_bytes(int64_t n, int64_t nq, int32_t k);
+int morna_knn_exact_sparse(const int64_t *row_off, const int32_t *cols, const float *vals, const double *pp, int64_t n,
+                           int32_t dim, int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
+                           int32_t *out_ids, double *out_dist, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------ batched search (tensor cores) */
 
 /* Leading dimension (in halves) of the fp16 tensor-core operand for `dim` features:

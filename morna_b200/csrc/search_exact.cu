@@ -270,6 +270,71 @@ extern "C" int morna_row_norms(const float *vectors, int64_t n, int32_t dim, int
     return MORNA_OK;
 }
 
+// Wide --features (a staged query of ld doubles no longer fits shared memory, ld * 8 > 200 KB, i.e. D > 25,600): the
+// same scan with the query read from global memory (L1/L2-resident: every warp of the grid reads the same vector).
+// Same lane/chunk partition, same sums, same bits.
+__global__ void __launch_bounds__(kScanThreads)
+angular_distances_wide_kernel(const float *__restrict__ vectors, const double *__restrict__ pp, int64_t n, int64_t ld,
+                              const double *__restrict__ queries, int64_t nq, int64_t q_ld, int32_t dim,
+                              double *__restrict__ dist, int64_t dist_ld) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t q = blockIdx.y;
+    const double *qsrc = queries + q * q_ld;
+    const int chunks = (int)(ld >> 2);
+    double qq = 0.0;
+    for (int c = lane; c < chunks; c += 32) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const double a = 4 * c + t < dim ? __ldg(qsrc + 4 * c + t) : 0.0;
+            qq = fma(a, a, qq);
+        }
+    }
+    qq = warp_sum(qq);
+    const int64_t warps_total = (int64_t)gridDim.x * kScanWarps;
+    for (int64_t row = (int64_t)blockIdx.x * kScanWarps + warp; row < n; row += warps_total) {
+        const float4 *src = reinterpret_cast<const float4 *>(vectors + row * ld);
+        double acc = 0.0;
+        int c = lane;
+        for (; c + 96 < chunks; c += 128) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = ldg_stream_f4(src + c + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = 4 * (c + 32 * u);
+                const double q0 = e < dim ? __ldg(qsrc + e) : 0.0, q1 = e + 1 < dim ? __ldg(qsrc + e + 1) : 0.0;
+                const double q2 = e + 2 < dim ? __ldg(qsrc + e + 2) : 0.0, q3 = e + 3 < dim ? __ldg(qsrc + e + 3) : 0.0;
+                acc = fma((double)v[u].x, q0, acc); acc = fma((double)v[u].y, q1, acc);
+                acc = fma((double)v[u].z, q2, acc); acc = fma((double)v[u].w, q3, acc);
+            }
+        }
+        for (; c < chunks; c += 32) {
+            const float4 v = ldg_stream_f4(src + c);
+            const int e = 4 * c;
+            const double q0 = e < dim ? __ldg(qsrc + e) : 0.0, q1 = e + 1 < dim ? __ldg(qsrc + e + 1) : 0.0;
+            const double q2 = e + 2 < dim ? __ldg(qsrc + e + 2) : 0.0, q3 = e + 3 < dim ? __ldg(qsrc + e + 3) : 0.0;
+            acc = fma((double)v.x, q0, acc); acc = fma((double)v.y, q1, acc);
+            acc = fma((double)v.z, q2, acc); acc = fma((double)v.w, q3, acc);
+        }
+        const double pq = warp_sum(acc);
+        if (lane == 0) dist[q * dist_ld + row] = angular_from_sums(pp[row], qq, pq);
+    }
+}
+
+static int launch_distances_wide(const float *vectors, const double *pp, int64_t n, int32_t dim, int64_t ld,
+                                 const double *queries, int64_t nq, int64_t q_ld, double *dist, int64_t dist_ld,
+                                 cudaStream_t stream) {
+    if (nq > 65535) return MORNA_ERR_INVALID_ARGUMENT;
+    int64_t blocks = (n + kScanWarps - 1) / kScanWarps;
+    int64_t cap = ((int64_t)sm_count_cached() * 8 + nq - 1) / nq;
+    if (cap < 1) cap = 1;
+    if (blocks > cap) blocks = cap;
+    dim3 grid((unsigned)blocks, (unsigned)nq);
+    angular_distances_wide_kernel<<<grid, kScanThreads, 0, stream>>>(vectors, pp, n, ld, queries, nq, q_ld, dim, dist, dist_ld);
+    MORNA_LAUNCH_CHECK();
+    return MORNA_OK;
+}
+
 template <int QB>
 static int launch_distances(const float *vectors, const double *pp, int64_t n, int32_t dim, int64_t ld,
                             const double *queries, int64_t nq, int64_t q_ld, double *dist,
@@ -313,8 +378,12 @@ extern "C" int morna_angular_distances(const float *vectors, const double *pp, i
                                      dist + done * dist_ld, dist_ld, s);
         else {
             take = std::min<int64_t>(left, 65535);
-            rc = launch_distances<1>(vectors, pp, n, dim, ld, queries + done * q_ld, take, q_ld,
-                                     dist + done * dist_ld, dist_ld, s);
+            if ((size_t)ld * sizeof(double) <= 200 * 1024)
+                rc = launch_distances<1>(vectors, pp, n, dim, ld, queries + done * q_ld, take, q_ld,
+                                         dist + done * dist_ld, dist_ld, s);
+            else
+                rc = launch_distances_wide(vectors, pp, n, dim, ld, queries + done * q_ld, take, q_ld,
+                                           dist + done * dist_ld, dist_ld, s);
         }
         if (rc != MORNA_OK) return rc;
         done += take;

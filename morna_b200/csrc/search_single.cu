@@ -496,7 +496,13 @@ extern "C" int morna_knn_single(const float *vectors, const double *pp, int64_t 
     const size_t tail_bytes = (size_t)kBins * 4 + (size_t)kS1Cand * (4 + 8 + 4);
     static_assert(kBins * 4 >= kS1List * 8, "the survivor lists overlay the histogram copy");
     if (smem < tail_bytes) smem = tail_bytes;
-    if (smem > 100 * 1024) return MORNA_ERR_INVALID_ARGUMENT;
+    if (smem > 100 * 1024) {
+        // very wide --features (D > 12,800): the staged query would not leave room for two CTAs per SM; the generic
+        // scan (morna_knn_exact, which reads a query this wide from global memory) answers -- same results
+        static const int32_t one = 1;
+        MORNA_CUDA_TRY(cudaMemcpyAsync(fallback, &one, sizeof(one), cudaMemcpyHostToDevice, s));
+        return MORNA_OK;
+    }
     // rows per warp, in passes of R rows.  Measured on B200 (scripts/single_rows_sweep.py): passes of three
     // rows with two chunk steps in flight beat one pass of the warp's whole share -- the first pass's
     // histogram atomics and distance stores overlap the second pass's loads instead of all landing at

@@ -1,0 +1,271 @@
+// Exact angular kNN over a SPARSE index: rows with a handful of non-zero buckets, which is what an index built
+// from few junctions looks like (the reference's own fixture tests/tiny_intropolis.tsv: 1-3 non-zeros in 3000
+// buckets, and thousands of rows parallel to each other).  On such data the tensor-core path is the wrong tool --
+// thousands of rows tie inside any fp16 error band, so every candidate list overflows -- while the exact FP64
+// distance of a (query, row) pair costs nnz(row) multiply-adds instead of D.  The distances computed here are
+// BIT-IDENTICAL to the dense scan's (morna_angular_distances): skipping a zero entry skips adding +-0 to a sum,
+// which never changes it, and the non-zero terms are added in the dense kernels' canonical order -- lane
+// (col/4)%32 accumulates its terms by ascending column, then the 32 lane sums meet in the fixed xor-butterfly,
+// emulated below on the few lanes that hold anything.  Replaces cosine_distance + the scan of exact_search_nn
+// (morna.py:101-114, 697-712) for sparse indexes; the top-k selection is morna_select_topk as in morna_knn_exact.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace morna {
+
+constexpr int kSparseMaxNnz = 16;        // rows with more non-zeros keep the index on the dense paths
+constexpr int kSparseThreads = 256;
+
+// qq with the canonical tree: one warp per query
+__global__ void __launch_bounds__(kSparseThreads)
+query_norms_kernel(const double *__restrict__ queries, int64_t nq, int64_t q_ld, int32_t dim, double *__restrict__ qq) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * (kSparseThreads / 32) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const double *src = queries + q * q_ld;
+    double acc = 0.0;
+    for (int c = lane; 4 * c < dim; c += 32) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const double a = 4 * c + t < dim ? src[4 * c + t] : 0.0;
+            acc = fma(a, a, acc);
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) qq[q] = acc;
+}
+
+// thread = (row, query): the row's non-zeros against the query, summed in the canonical order
+__global__ void __launch_bounds__(kSparseThreads)
+sparse_distances_kernel(const int64_t *__restrict__ row_off, const int32_t *__restrict__ cols, const float *__restrict__ vals,
+                        const double *__restrict__ pp, int64_t n, const double *__restrict__ queries, int64_t q_ld,
+                        const double *__restrict__ qq, double *__restrict__ dist, int64_t dist_ld) {
+    const int64_t row = (int64_t)blockIdx.x * kSparseThreads + threadIdx.x;
+    const int64_t q = blockIdx.y;
+    if (row >= n) return;
+    const double *qv = queries + q * q_ld;
+    const int64_t e0 = row_off[row], e1 = row_off[row + 1];
+    int lane_of[kSparseMaxNnz];
+    double sum_of[kSparseMaxNnz];
+    int m = 0;
+    for (int64_t e = e0; e < e1; ++e) {                      // ascending columns: each lane's terms in its own order
+        const int col = cols[e];
+        const int lane = (col >> 2) & 31;
+        const double prod_a = (double)vals[e], prod_b = __ldg(qv + col);
+        int j = 0;
+        while (j < m && lane_of[j] != lane) ++j;
+        if (j == m) { lane_of[m] = lane; sum_of[m] = 0.0; ++m; }
+        sum_of[j] = fma(prod_a, prod_b, sum_of[j]);
+    }
+    // the butterfly v += shfl_xor(v, 16), 8, 4, 2, 1: after a step the lanes that differ only in that bit hold the
+    // same value, so a lane class is its index with the bit cleared; x + 0 = x for the absent partner
+#pragma unroll
+    for (int bit = 16; bit > 0; bit >>= 1) {
+        for (int i = 0; i < m; ++i) {
+            for (int j = i + 1; j < m; ++j) {
+                if ((lane_of[i] ^ lane_of[j]) == bit) {                     // processed bits are already cleared in both
+                    sum_of[i] = sum_of[i] + sum_of[j];
+                    lane_of[j] = lane_of[m - 1]; sum_of[j] = sum_of[m - 1]; --m;
+                    break;
+                }
+            }
+            lane_of[i] &= ~bit;
+        }
+    }
+    const double pq = m > 0 ? sum_of[0] : 0.0;
+    dist[q * dist_ld + row] = angular_from_sums(pp[row], qq[q], pq);
+}
+
+// ---- exact top-k under massive ties ------------------------------------------------------------------------------
+// One CTA per query over its n distances.  A sparse index has few distinct distance values per query (thousands of
+// parallel rows), which defeats pivot-and-sort selection; a radix select does not care: the k-th smallest 64-bit key
+// is found digit by digit (11 bits a pass, 2048-bin shared histogram, warp-aggregated increments), then one pass in
+// DESCENDING row order keeps everything below it and, among the rows tied with it, the first `quota` met -- the highest
+// ids, which is the reference's tie rule (morna.py:705-712: equal distances, later row first).  The k survivors are
+// sorted under the full rule in shared memory.  Distances are >= 0 (or +inf), so their bit patterns order like the values.
+constexpr int kRsThreads = 1024, kRsWarps = kRsThreads / 32;
+constexpr int kRsBits = 11, kRsBins = 1 << kRsBits;
+constexpr int kRsMaxK = 2048;
+
+__global__ void __launch_bounds__(kRsThreads)
+select_radix_kernel(const double *__restrict__ dist, int64_t n, int64_t dist_ld, int32_t id_base, int32_t k,
+                    int32_t *__restrict__ out_ids, double *__restrict__ out_dist) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sd = reinterpret_cast<double *>(smem_raw);                 // [P] selected distances
+    int *si = reinterpret_cast<int *>(sd + kRsMaxK);                   // [P] selected ids
+    __shared__ unsigned int hist[kRsBins];
+    __shared__ unsigned int warp_tot[kRsWarps];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_need, s_count, s_ties;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double *row = dist + (int64_t)blockIdx.x * dist_ld;
+    int32_t *oi = out_ids + (int64_t)blockIdx.x * k;
+    double *od = out_dist + (int64_t)blockIdx.x * k;
+    const int kk = (int)min((int64_t)k, n);
+    if (kk == 0) {
+        for (int i = tid; i < k; i += kRsThreads) { oi[i] = -1; od[i] = INFINITY; }
+        return;
+    }
+    if (tid == 0) { s_prefix = 0ull; s_need = kk; s_count = 0; s_ties = 0; }
+    unsigned long long mask = 0ull;
+    for (int shift = 64 - kRsBits; ; shift -= kRsBits) {               // digits at bits 53, 42, 31, 20, 9 and the last 9 bits
+        const int width = shift >= 0 ? kRsBits : kRsBits + shift;
+        const int sh = shift >= 0 ? shift : 0;
+        const unsigned int bins = 1u << width;
+        for (int b = tid; b < kRsBins; b += kRsThreads) hist[b] = 0u;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        for (int64_t i0 = 0; i0 < n; i0 += kRsThreads) {
+            const int64_t i = i0 + tid;
+            unsigned int digit = 0xffffffffu;
+            if (i < n) {
+                const unsigned long long key = (unsigned long long)__double_as_longlong(row[i]);
+                if ((key & mask) == prefix) digit = (unsigned int)(key >> sh) & (bins - 1u);
+            }
+            const unsigned int peers = __match_any_sync(kFull, digit);
+            if (digit != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
+        }
+        __syncthreads();
+        // the bin in which the cumulative count reaches s_need: every thread owns two consecutive bins
+        const unsigned int h0 = hist[2 * tid], h1 = hist[2 * tid + 1];
+        unsigned int incl = h0 + h1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        unsigned int before = incl - (h0 + h1);
+        for (int w = 0; w < warp; ++w) before += warp_tot[w];
+        const unsigned int need = (unsigned int)s_need;
+        __syncthreads();                                               // everyone has read s_need / warp_tot
+        if (before < need && need <= before + h0 + h1) {
+            const int bin = need <= before + h0 ? 2 * tid : 2 * tid + 1;
+            s_need = (int)(need - (bin == 2 * tid ? before : before + h0));
+            s_prefix = prefix | ((unsigned long long)bin << sh);
+        }
+        mask |= (unsigned long long)(bins - 1u) << sh;
+        __syncthreads();
+        if (shift <= 0) break;
+    }
+    const unsigned long long key_k = s_prefix;                         // the kk-th smallest key
+    const int quota = s_need;                                          // how many of the rows tied with it belong to the answer
+    // descending row order: everything below key_k, and the first `quota` ties met
+    for (int64_t top = n; top > 0; top -= kRsThreads) {
+        const int64_t i = top - 1 - tid;
+        bool less = false, tie = false;
+        double d = 0.0;
+        if (i >= 0) {
+            d = row[i];
+            const unsigned long long key = (unsigned long long)__double_as_longlong(d);
+            less = key < key_k; tie = key == key_k;
+        }
+        const unsigned int tie_mask = __ballot_sync(kFull, tie);
+        if (lane == 0) warp_tot[warp] = __popc(tie_mask);
+        __syncthreads();
+        int tie_rank = s_ties + __popc(tie_mask & ((1u << lane) - 1u));
+        int block_ties = 0;
+        for (int w = 0; w < kRsWarps; ++w) { if (w < warp) tie_rank += warp_tot[w]; block_ties += warp_tot[w]; }
+        const bool take = less || (tie && tie_rank < quota);
+        const unsigned int take_mask = __ballot_sync(kFull, take);
+        int base = 0;
+        if (lane == 0 && take_mask) base = atomicAdd(&s_count, __popc(take_mask));
+        base = __shfl_sync(kFull, base, 0);
+        if (take) {
+            const int at = base + __popc(take_mask & ((1u << lane) - 1u));
+            if (at < kRsMaxK) { sd[at] = d; si[at] = id_base + (int)i; }
+        }
+        __syncthreads();
+        if (tid == 0) s_ties += block_ties;
+        __syncthreads();
+    }
+    const int count = min(s_count, kRsMaxK);                           // == kk
+    int P = 32;
+    while (P < count) P <<= 1;
+    for (int i = count + tid; i < P; i += kRsThreads) { sd[i] = INFINITY; si[i] = -1; }
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = tid; i < (P >> 1); i += kRsThreads) {
+                const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                const bool asc = (lo & size) == 0;
+                const double dl = sd[lo], dh = sd[hi];
+                const int il = si[lo], ih = si[hi];
+                const bool swap = asc ? before(dh, ih, dl, il) : before(dl, il, dh, ih);
+                if (swap) { sd[lo] = dh; sd[hi] = dl; si[lo] = ih; si[hi] = il; }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < k; i += kRsThreads) {
+        const bool ok = i < count && si[i] >= 0;
+        oi[i] = ok ? si[i] : -1;
+        od[i] = ok ? sd[i] : INFINITY;
+    }
+}
+
+static int64_t sparse_query_tile(int64_t n, int64_t nq) {
+    const int64_t budget = (int64_t)256 << 20;   // bytes of distance scratch per tile
+    int64_t t = budget / (8 * (n > 0 ? n : 1));
+    if (t < 1) t = 1;
+    if (t > 16384) t = 16384;
+    if (t > nq) t = nq;
+    return t > 0 ? t : 1;
+}
+
+}  // namespace morna
+
+using namespace morna;
+
+extern "C" int32_t morna_sparse_max_nnz(void) { return kSparseMaxNnz; }
+
+extern "C" size_t morna_knn_exact_sparse_workspace_bytes(int64_t n, int64_t nq, int32_t k) {
+    const int64_t tile = sparse_query_tile(n, nq);
+    return align_up((size_t)tile * (size_t)(n > 0 ? n : 1) * sizeof(double), 256) + align_up((size_t)(nq > 0 ? nq : 1) * sizeof(double), 256) +
+           morna_select_topk_workspace_bytes(n, tile, k) + 256;
+}
+
+extern "C" int morna_knn_exact_sparse(const int64_t *row_off, const int32_t *cols, const float *vals, const double *pp, int64_t n,
+                                      int32_t dim, int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
+                                      int32_t *out_ids, double *out_dist, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!row_off || !cols || !vals || !pp || !queries || !out_ids || !out_dist || n <= 0 || nq < 0 || dim <= 0 || q_ld < dim || k <= 0)
+        return MORNA_ERR_INVALID_ARGUMENT;
+    if (!workspace || workspace_bytes < morna_knn_exact_sparse_workspace_bytes(n, nq, k)) return MORNA_ERR_WORKSPACE_TOO_SMALL;
+    if (nq == 0) return MORNA_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t tile = sparse_query_tile(n, nq);
+    unsigned char *ws = (unsigned char *)workspace;
+    double *dist = (double *)ws;
+    const size_t dist_bytes = align_up((size_t)tile * (size_t)n * sizeof(double), 256);
+    double *qq = (double *)(ws + dist_bytes);
+    const size_t qq_bytes = align_up((size_t)nq * sizeof(double), 256);
+    void *sel_ws = ws + dist_bytes + qq_bytes;
+    const size_t sel_bytes = workspace_bytes - dist_bytes - qq_bytes;
+    query_norms_kernel<<<(unsigned)((nq + kSparseThreads / 32 - 1) / (kSparseThreads / 32)), kSparseThreads, 0, s>>>(queries, nq, q_ld, dim, qq);
+    MORNA_LAUNCH_CHECK();
+    for (int64_t q0 = 0; q0 < nq; q0 += tile) {
+        const int64_t cnt = nq - q0 < tile ? nq - q0 : tile;
+        for (int64_t y0 = 0; y0 < cnt; y0 += 65535) {         // grid.y limit
+            const int64_t ny = cnt - y0 < 65535 ? cnt - y0 : 65535;
+            dim3 grid((unsigned)((n + kSparseThreads - 1) / kSparseThreads), (unsigned)ny);
+            sparse_distances_kernel<<<grid, kSparseThreads, 0, s>>>(row_off, cols, vals, pp, n, queries + (q0 + y0) * q_ld, q_ld,
+                                                                   qq + q0 + y0, dist + y0 * n, n);
+            MORNA_LAUNCH_CHECK();
+        }
+        if (k <= kRsMaxK && n <= 0x7fffffff) {
+            const size_t smem = (size_t)kRsMaxK * (sizeof(double) + sizeof(int));
+            select_radix_kernel<<<(unsigned)cnt, kRsThreads, smem, s>>>(dist, n, n, id_base, k, out_ids + q0 * k, out_dist + q0 * k);
+            MORNA_LAUNCH_CHECK();
+            continue;
+        }
+        for (int64_t y0 = 0; y0 < cnt; y0 += 65535) {
+            const int64_t ny = cnt - y0 < 65535 ? cnt - y0 : 65535;
+            int rc = morna_select_topk(dist + y0 * n, nullptr, n, n, id_base, ny, k, out_ids + (q0 + y0) * k, out_dist + (q0 + y0) * k,
+                                       sel_ws, sel_bytes, stream);
+            if (rc != MORNA_OK) return rc;
+        }
+    }
+    return MORNA_OK;
+}

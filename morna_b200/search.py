@@ -79,6 +79,39 @@ class MornaSearch(object):
         with torch.cuda.device(dev):
             _lib.check(self.lib.morna_row_norms(_lib.dev_ptr(self.vectors), n, self.dim, self.ld,
                                                 _lib.dev_ptr(self.pp), _lib.stream_ptr()), "morna_row_norms")
+        self._build_csr()
+
+    def _build_csr(self):
+        """A sparse index (every row has at most morna_sparse_max_nnz() non-zero buckets -- an index built from a handful
+        of junctions, like the reference's fixture) also keeps its rows in CSR form: exact search then costs nnz(row)
+        multiply-adds per (query, row) instead of D, with the same bits (morna_knn_exact_sparse).  Index-load time,
+        not the hot path: plain torch ops."""
+        self.csr = None
+        n = self.row_hi - self.row_lo
+        if n == 0:
+            return
+        nz = self.vectors != 0
+        counts = nz.sum(dim=1)
+        if int(counts.max()) > int(self.lib.morna_sparse_max_nnz()):
+            return
+        where = nz.nonzero()                               # row-major: columns ascending within a row
+        row_off = torch.zeros(n + 1, dtype=torch.int64, device=self.device)
+        row_off[1:] = counts.cumsum(0)
+        cols = where[:, 1].to(torch.int32).contiguous()
+        vals = self.vectors[where[:, 0], where[:, 1]].contiguous()
+        if cols.numel() == 0:                              # all-zero index: keep valid pointers
+            cols = torch.zeros(1, dtype=torch.int32, device=self.device)
+            vals = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.csr = (row_off, cols, vals)
+        # Which path answers a batch.  Rows with the same non-zero buckets can be parallel to each other (one bucket:
+        # always), i.e. tie from every query's point of view; when the largest such group is wider than the tensor
+        # path's candidate lists, its queries would all overflow into the exact scan -- then the CSR exact path answers
+        # directly.  Otherwise the tensor-core path is faster even on sparse rows.
+        pos = torch.arange(where.shape[0], device=self.device) - row_off[where[:, 0]]
+        sig = torch.zeros(n, dtype=torch.int64, device=self.device)
+        sig.index_add_(0, where[:, 0], (where[:, 1] + 1) * torch.pow(torch.tensor(1000003, device=self.device), pos))
+        self.largest_tie_group = int(torch.unique(sig, return_counts=True)[1].max())
+        self.sparse_exact = self.largest_tie_group >= self.TIE_GROUP_FOR_SPARSE_PATH
 
     # ------------------------------------------------------------------ query construction
     def inverse_lookup(self, internal_id):
@@ -169,6 +202,8 @@ class MornaSearch(object):
         return out_ids, out_d
 
     MAX_SELECT_K = 2048              # kSelMaxK of morna_select_topk
+    sparse_exact = False             # set at load for a sparse index whose tie groups would overflow the tensor path's lists
+    TIE_GROUP_FOR_SPARSE_PATH = 512  # (the final candidate lists hold 1024 rows; a query usually sees two or more such groups)
 
     def exact_search_device(self, queries, k, stream=None, allow_single=True):
         """queries: CUDA float64 [nq x dim].  Returns device (ids int32 [nq x k], dists float64 [nq x k]); ids are
@@ -191,14 +226,25 @@ class MornaSearch(object):
         k_eff = min(k, n)
         if n == 0 or nq == 0 or k_eff == 0:
             return out_ids, out_d
-        if nq == 1 and allow_single and k_eff <= 512:
+        if nq == 1 and allow_single and k_eff <= 512 and self.csr is None:
             return self.single_search_device(queries[0], k)
         with torch.cuda.device(dev):
             if k_eff > self.MAX_SELECT_K:
                 return self._full_sort_search(queries, k, out_ids, out_d)
-            ws = self._workspace(self.lib.morna_knn_exact_workspace_bytes(n, nq, k_eff))
             ids_k = out_ids if k_eff == k else torch.empty((nq, k_eff), dtype=torch.int32, device=dev)
             d_k = out_d if k_eff == k else torch.empty((nq, k_eff), dtype=torch.float64, device=dev)
+            if self.csr is not None and bool(torch.isfinite(queries).all()):
+                row_off, cols, vals = self.csr
+                ws = self._workspace(self.lib.morna_knn_exact_sparse_workspace_bytes(n, nq, k_eff), "sparse")
+                _lib.check(self.lib.morna_knn_exact_sparse(
+                    _lib.dev_ptr(row_off), _lib.dev_ptr(cols), _lib.dev_ptr(vals), _lib.dev_ptr(self.pp), n, self.dim, self.row_lo,
+                    _lib.ptr(queries), nq, q_ld, k_eff, _lib.dev_ptr(ids_k), _lib.dev_ptr(d_k), _lib.dev_ptr(ws), ws.numel(),
+                    _lib.stream_ptr()), "morna_knn_exact_sparse")
+                if k_eff != k:
+                    out_ids[:, :k_eff] = ids_k
+                    out_d[:, :k_eff] = d_k
+                return out_ids, out_d
+            ws = self._workspace(self.lib.morna_knn_exact_workspace_bytes(n, nq, k_eff))
             _lib.check(self.lib.morna_knn_exact(
                 _lib.dev_ptr(self.vectors), _lib.dev_ptr(self.pp), n, self.dim, self.ld, self.row_lo,
                 _lib.ptr(queries), nq, q_ld, k_eff, _lib.dev_ptr(ids_k), _lib.dev_ptr(d_k),
@@ -286,6 +332,8 @@ class MornaSearch(object):
                 sub.__dict__.update(self.__dict__)
                 sub.vectors, sub.pp = self.vectors[b0:b1], self.pp[b0:b1]
                 sub.row_lo, sub.row_hi, sub._ws_pool = self.row_lo + b0, self.row_lo + b1, {}
+                if (b0, b1) != (0, self.row_hi - self.row_lo):
+                    sub.csr = None                          # (the CSR form covers the whole resident block)
                 e_ids, e_d = sub.exact_search_device(queries[idx], k, stream, allow_single=False)
                 out_ids[idx] = e_ids
                 out_d[idx] = e_d
@@ -306,8 +354,8 @@ class MornaSearch(object):
         nq = queries.shape[0]
         n = self.row_hi - self.row_lo
         assert queries.shape[1] == self.dim
-        if n == 0 or nq == 0 or k > 512 or k <= 0 or k > n:
-            return self.exact_search_device(queries, k, stream)
+        if n == 0 or nq == 0 or k > 512 or k <= 0 or k > n or (self.csr is not None and self.sparse_exact):
+            return self.exact_search_device(queries, k, stream)     # (a sparse index: its ties would overflow every list)
         parts = self._batched_launch(queries, k, stream, phase_events)
         if check_overflow:
             return self._batched_finish(parts, queries, k, stream)
@@ -581,7 +629,7 @@ class BatchPipeline(object):
             prev, self.unranked = self.unranked, None
             sl.parts = sl.job = None
             sl.mode = "plain"
-            if n == 0 or sl.nq == 0 or k > 512 or k <= 0 or k > n:
+            if n == 0 or sl.nq == 0 or k > 512 or k <= 0 or k > n or (s.csr is not None and s.sparse_exact):
                 if prev is not None:
                     self._rerank(prev, resume=False)
                 ids, d = s.exact_search_device(sl.qd, k)

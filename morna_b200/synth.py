@@ -53,7 +53,12 @@ def sparse(n, dim, device, seed=1234, junctions=40, max_nnz=3):
     return out
 
 
-KINDS = {"gauss": gauss, "tissue": tissue, "sparse": sparse}
+def sparse_fixture(n, dim, device, seed=1234):
+    """Three junctions in all, as in tests/tiny_intropolis.tsv: about a third of the rows are parallel to any query."""
+    return sparse(n, dim, device, seed, junctions=3, max_nnz=3)
+
+
+KINDS = {"gauss": gauss, "tissue": tissue, "sparse": sparse, "sparse_fixture": sparse_fixture}
 
 
 def matrix(kind, n, dim, device, seed=1234):

@@ -122,6 +122,8 @@ def test_batched_with_massive_ties_falls_back_to_exact_scan():
     oracle = mo.go_index(tiny_lines(), features=3000, sample_threshold=100)
     S = oracle.matrix_f32()
     srch = make_search(S)
+    assert srch.csr is not None
+    srch.sparse_exact = False                # force the tensor-core path (a sparse index normally skips it)
     rows = np.array([0, 2040, 6595, 5, 4000, 17])
     q = torch.from_numpy(S[rows].astype(np.float64)).cuda()
     e_ids, e_d = srch.exact_search_device(q, 20)
@@ -241,6 +243,7 @@ def test_streaming_batches_handle_tie_overflow_and_row_blocks():
     oracle = mo.go_index(tiny_lines(), features=3000, sample_threshold=100)
     S = oracle.matrix_f32()
     srch = make_search(S)
+    srch.sparse_exact = False                        # force the tensor-core path on this sparse index
     srch.BATCH_BLOCK_ROWS = 4096                     # two row blocks + merge, and thousands of ties at distance 0
     rows = np.array([0, 2040, 6595, 5, 4000, 17] * 12)
     B = S[rows]
@@ -328,3 +331,79 @@ def test_large_and_small_k_on_every_path(k):
         assert torch.equal(s_ids[0], e_ids[j]) and torch.equal(s_d[0], e_d[j])
     true_d = c_oracle.distances(S, Q[3])
     check_topk(true_d, b_ids[3].cpu().numpy(), b_d[3].cpu().numpy(), tol=1e-9)
+
+
+def _dense_twin(srch):
+    """The same index without its CSR form: every search goes through the dense kernels."""
+    from morna_b200.search import MornaSearch
+    twin = MornaSearch.__new__(MornaSearch)
+    twin.__dict__.update(srch.__dict__)
+    twin.csr, twin._ws_pool = None, {}
+    return twin
+
+
+def test_sparse_exact_path_is_bit_identical_on_the_reference_fixture():
+    """tests/tiny_intropolis.tsv through morna index: 6850 rows with 1-3 non-zero buckets, 3737 of them tie at distance
+    0 from a typical query.  The CSR exact path (nnz multiply-adds per pair) returns the dense scan's bits and the
+    oracle's golden lists; batches, single queries and the streaming API all take it."""
+    oracle = mo.go_index(tiny_lines(), features=3000, sample_threshold=100)
+    S = oracle.matrix_f32()
+    srch = make_search(S)
+    assert srch.csr is not None and srch.sparse_exact and srch.largest_tie_group > 1000
+    dense = _dense_twin(srch)
+    rng = np.random.default_rng(3)
+    rows = np.concatenate([[0, 2040, 6595, 5, 4000, 17], rng.permutation(S.shape[0])[:250]])
+    Q = S[rows].astype(np.float64)
+    Q[10:20] += 0.01 * rng.standard_normal((10, 3000))          # dense, out-of-index queries
+    Q[20, :] = 0.0
+    q = torch.from_numpy(Q).cuda()
+    for k in (1, 20, 100, 600):
+        s_ids, s_d = srch.batched_search_device(q, k)
+        d_ids, d_d = dense.exact_search_device(q, k, allow_single=False)
+        assert torch.equal(s_ids, d_ids) and torch.equal(s_d, d_d)
+    one_i, one_d = srch.exact_search_device(q[:1], 20)
+    with open(os.path.join(GOLDEN, "tiny_expected.json")) as fh:
+        exp = json.load(fh)
+    assert one_i[0].tolist() == exp["queries"][0]["ids"]
+    got = list(srch.search_batches([Q, Q.astype(np.float32)], 20))
+    w_i, w_d = dense.exact_search_device(q, 20, allow_single=False)
+    assert np.array_equal(got[0][0], w_i.cpu().numpy()) and np.array_equal(got[0][1], w_d.cpu().numpy())
+
+
+@pytest.mark.parametrize("n,d,max_nnz", [(5000, 3000, 3), (3000, 130, 16), (2000, 7, 4), (4000, 40000, 8)])
+def test_sparse_exact_path_matches_dense_kernels_bit_for_bit(n, d, max_nnz):
+    """Synthetic sparse rows with up to 16 non-zeros (several per summation lane, negative zeros, float32 denormals,
+    all-zero rows, wide feature counts): CSR exact search == dense exact search, ids and distance bits, and one query
+    against the oracle."""
+    rng = np.random.default_rng(n + d)
+    S = np.zeros((n, d), np.float32)
+    for i in range(n):
+        m = int(rng.integers(0, min(max_nnz, d) + 1))
+        cols = rng.choice(d, size=m, replace=False)
+        if m and rng.random() < 0.3:                                   # several entries in one lane class
+            cols = (cols[0] // 4 * 4 + 128 * np.arange(m)) % d
+            cols = np.unique(cols)
+        S[i, cols] = (rng.integers(1, 50, size=len(cols)) * rng.choice([-1.0, 1.0], size=len(cols))
+                      * rng.choice([0.098, 1.21, 1.415, 0.5], size=len(cols))).astype(np.float32)
+    S[3, :2] = np.float32(1e-42)
+    S[4, 0] = np.float32(-0.0)
+    srch = make_search(S)
+    assert srch.csr is not None
+    dense = _dense_twin(srch)
+    nq = 97
+    Q = np.concatenate([S[rng.permutation(n)[:60]].astype(np.float64), rng.standard_normal((nq - 60, d))])
+    Q[1] = 0.0
+    Q[2, : min(d, 5)] = -0.0
+    q = torch.from_numpy(Q).cuda()
+    for k in (1, 33):
+        s_ids, s_d = srch.exact_search_device(q, k)
+        d_ids, d_d = dense.exact_search_device(q, k, allow_single=False)
+        assert torch.equal(s_ids, d_ids) and torch.equal(s_d, d_d)
+    true_d = c_oracle.distances(S, Q[70])
+    check_topk(true_d, s_ids[70].cpu().numpy(), s_d[70].cpu().numpy(), tol=1e-9)
+    # a non-finite query value keeps the dense arithmetic (0 * inf = nan there)
+    Q[5, 0] = np.inf
+    q = torch.from_numpy(Q[:8]).cuda()
+    s_ids, s_d = srch.exact_search_device(q, 5)
+    d_ids, d_d = dense.exact_search_device(q, 5, allow_single=False)
+    assert torch.equal(s_ids, d_ids)

@@ -178,6 +178,29 @@ def test_same_sign_rows_wide_features_stay_within_eps_and_equal_oracle():
                               "same-sign")
 
 
+@pytest.mark.parametrize("d", [10000, 30000])
+def test_every_search_path_at_wide_features_equals_oracle(d):
+    """--features up to 30,000 (morna.py:982-986; BASELINE configs[4] sweeps that far): the batched tensor-core path,
+    the single-query call and the generic FP64 scan all answer an index this wide, and agree with the oracle."""
+    n, nq, k = 2500, 96, 40
+    S = synth.gauss(n, d, "cuda", seed=d)
+    srch = make_search(S)
+    q_in, rows = synth.queries(S, nq // 2)
+    q_out, _ = synth.queries(S, nq // 2, noise=0.05)
+    q = torch.cat([q_in, q_out]).contiguous()
+    b_ids, b_d = srch.batched_search_device(q, k)
+    assert srch.last_stats[0] == 0
+    e_ids, e_d = srch.exact_search_device(q, k, allow_single=False)
+    assert torch.equal(b_ids, e_ids) and torch.equal(b_d, e_d)
+    for j in (0, nq - 1):
+        s_ids, s_d = srch.single_search_device(q[j], k)
+        assert torch.equal(s_ids[0], e_ids[j]) and torch.equal(s_d[0], e_d[j])
+    pick = np.arange(0, nq, 12)
+    assert_lists_equal_oracle(S.cpu().numpy(), q.cpu().numpy()[pick], b_ids.cpu().numpy()[pick], b_d.cpu().numpy()[pick], k,
+                              "D=%d" % d)
+    assert b_ids[: nq // 2, 0].tolist() == rows.tolist()
+
+
 # ------------------------------------------------------------------ multi-process NCCL (needs >= 2 GPUs)
 def _free_port():
     s = socket.socket()
