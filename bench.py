@@ -295,7 +295,26 @@ def main():
     roofline["step_algorithmic"] = "2*Q*N*D flops / ms_per_step (prep, thresholds, top-k and re-rank included), Q=%d N=%d D=%d" % (nq, n_samples, DIM)
 
     note("end to end and phases timed")
+    # ---- approximate mode (the tensor-core pass without the exact re-rank): throughput and recall@k against the exact lists
+    approx = None
+    if rank == 0:
+        exact_ids, _ = srch.batched_search_device(queries64, K)
+        for _ in range(3):
+            a_ids, _a_d = srch.approx_search_device(queries64, K)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            a_ids, _a_d = srch.approx_search_device(queries64, K)
+        e1.record(); torch.cuda.synchronize()
+        both = torch.cat([exact_ids, a_ids], dim=1).sort(dim=1).values
+        recall = float((both[:, 1:] == both[:, :-1]).sum()) / float(nq * K)
+        approx = {"queries_per_s": nq / (e0.elapsed_time(e1) / 10 / 1e3), "ms_per_step": e0.elapsed_time(e1) / 10,
+                  "recall_at_k": recall, "k": K,
+                  "what": "MornaSearch.approx_search_device: top-k by fp16 tensor-core score, no FP64 re-rank; recall against the exact lists "
+                          "of the same queries (the reference's approximate mode is Annoy, n/a here)"}
     extras = {}
+    if approx is not None:
+        extras["approximate"] = approx
     full = not args.only_headline and n_samples == N_SAMPLES and nq == N_QUERIES
     if full:
         extras["datasets"] = dataset_lines(torch, synth, MornaSearch, device, rank, max_over_ranks, world)

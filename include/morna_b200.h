@@ -16,7 +16,9 @@
  *     size the matching *_workspace_bytes() function reports.
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
  *     the call returns without synchronising unless stated otherwise.
- *   - No global mutable state: calls on different streams / threads are independent.
+ *   - Calls on different streams / host threads / devices are independent.  The only process-wide state is (a) a
+ *     mutex-protected cache, per device ordinal, of the SM count and of each kernel's shared-memory opt-in, and
+ *     (b) the experiment knobs of morna_debug_set_tuning (tests and tuning scripts only; set them before searching).
  *   - Row-major matrices carry an explicit leading dimension `ld` in elements.
  *     Sample vectors: float32, ld % 4 == 0, pad columns [dim, ld) must be zero.
  */
@@ -283,6 +285,16 @@ int morna_knn_batched_rerank(const float *vectors, const double *pp, int64_t n, 
                              int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
                              int32_t *out_ids, double *out_dist, const uint8_t *overflow, void *workspace,
                              size_t workspace_bytes, int32_t resume, void *stream);
+
+/* Approximate mode (the reference's default search asks Annoy for approximate neighbours, morna.py:632-678; there is
+ * no forest here): the k best rows by fp16 tensor-core score, WITHOUT the exact re-rank -- the scoring half of
+ * morna_knn_batched followed by a per-query sort of the first-pass list.  Ids can differ from the exact answer where
+ * two cosines are closer than the fp16 error (recall@k is measured against morna_knn_batched by bench.py and the
+ * tests); distances are sqrt(2 - 2 score), off by up to ~1e-4.  Same workspace, overflow and stats as morna_knn_batched. */
+int morna_knn_batched_approx(const void *hs, int64_t ld_h, const float *rho_max, int64_t n, int32_t dim,
+                             int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
+                             int32_t *out_ids, double *out_dist, uint8_t *overflow, int32_t *stats,
+                             void *workspace, size_t workspace_bytes, void *stream);
 
 /* Test hook: raw fp16 tensor-core scores [nq x n] (n <= 8192) and the per-query bound eps. */
 int morna_debug_tensor_scores(const void *hs, int64_t ld_h, const float *rho_max, int64_t n, int32_t dim,

@@ -74,6 +74,8 @@ _SIGNATURES = {
                                          _c_vp, _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_vp, _c_vp]),
     "morna_knn_batched_score": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp, _c_i64, _c_i64, _c_i32,
                                                _c_vp, _c_vp, _c_vp, _c_sz, _c_vp, ctypes.POINTER(RerankJob), _c_vp, _c_vp]),
+    "morna_knn_batched_approx": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp, _c_i64, _c_i64, _c_i32,
+                                                _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_vp]),
     "morna_union_kth_bound": (ctypes.c_int, [_c_vp, _c_i32, _c_i64, _c_i32, _c_vp, _c_vp]),
     "morna_knn_batched_finalize": (ctypes.c_int, [_c_i64, _c_i64, _c_i32, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_vp]),
     "morna_knn_batched_rerank": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i32, _c_i64, _c_i32, _c_vp, _c_i64, _c_i64, _c_i32,

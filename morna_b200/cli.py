@@ -5,11 +5,12 @@ Kept: every flag of the two subcommands, stdin for the query, the
 "rank.<TAB>id[<TAB>distance][<TAB>metadata]" result lines with Python 2's float
 formatting, progress messages, the two extra stdout lines of -q.
 Different on purpose: without -e the reference asks Annoy for approximate
-neighbours; there is no forest here, so every search is the exact search
-(--search-k, --n-trees, -b are accepted and ignored).  `-q ID -e` runs the exact
+neighbours; there is no forest here -- the approximate mode is the tensor-core
+scoring pass without the exact re-rank (MornaSearch.search_nn; --search-k,
+--n-trees, -b are accepted and ignored), -e is the exact search.  `-q ID -e` runs the exact
 search with the stored row as the query (the reference ignores -e after -q).
-The `junctions` subcommand, -m metadata indexing and the convergence back-off
-loop are outside the hot path and exit with a message.
+-m works as in the reference (index: metadata file -> <basename>.meta.mor; search: keywords joined to the results).
+The `junctions` subcommand and the convergence back-off loop are outside the hot path and exit with a message.
 """
 import argparse
 import sys
@@ -24,6 +25,8 @@ def py2_str(v):
         if s.lstrip("-").isdigit():
             s += ".0"
         return s
+    if isinstance(v, tuple) and len(v) == 1 and isinstance(v[0], str):
+        return "(u" + repr(v[0]) + ",)"          # a metadata row as Python 2 prints the sqlite tuple of one unicode string
     return str(v)
 
 
@@ -86,7 +89,7 @@ def build_parser():
     index_parser.add_argument("-v", "--verbose", action="store_const", const=True, default=False,
                               help="be talkative")
     index_parser.add_argument("-m", "--metafile", metavar="<file>", type=str, required=False, default=None,
-                              help="metadata file (not indexed by this implementation)")
+                              help="metadata file: sample id then keywords per line; stored in <basename>.meta.mor for search -m")
     add_search_parameters(search_parser)
     return parser
 
@@ -135,8 +138,10 @@ def main(argv=None, stdin=None, stdout=None, stderr=None):
     searcher.finalize_query()
     if args.verbose:
         stderr.write("\n")
-    results = searcher.exact_search_nn(args.results, include_distances=args.distances,
-                                       meta_db=args.metadata)   # :1477-1479
+    if args.exact:                                              # :1477-1483
+        results = searcher.exact_search_nn(args.results, include_distances=args.distances, meta_db=args.metadata)
+    else:
+        results = searcher.search_nn(args.results, args.search_k, include_distances=args.distances, meta_db=args.metadata)
     results_output(results, stdout)
     return 0
 

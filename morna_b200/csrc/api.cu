@@ -1,5 +1,8 @@
 // Library-wide entry points: version, status names, launch counter, device probe.
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "common.cuh"
 
@@ -7,6 +10,35 @@ namespace morna {
 thread_local int g_last_cuda_error = 0;
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static std::mutex g_device_cache_mutex;
+
+int sm_count_current() {
+    static std::map<int, int> sms;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_device_cache_mutex);
+    int &v = sms[dev];
+    if (v <= 0) {
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (v <= 0) v = 148;
+    }
+    return v;
+}
+
+int ensure_dynamic_smem(const void *kernel, size_t bytes) {
+    static std::map<std::pair<const void *, int>, size_t> granted;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_device_cache_mutex);
+    size_t &have = granted[std::make_pair(kernel, dev)];
+    if (bytes > have) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return cuda_fail(e);
+        have = bytes;
+    }
+    return MORNA_OK;
+}
 }  // namespace morna
 
 extern "C" int morna_abi_version(void) { return MORNA_ABI_VERSION; }

@@ -9,6 +9,10 @@ namespace morna {
 
 extern thread_local int g_last_cuda_error;
 void count_launch(int n = 1);
+// SM count of the current device and the dynamic-shared-memory opt-in of a kernel, both cached per device ordinal
+// behind a mutex (function attributes are per device; several host threads / GPUs may call in)
+int sm_count_current();
+int ensure_dynamic_smem(const void *kernel, size_t bytes);
 
 inline int cuda_fail(cudaError_t e) {
     g_last_cuda_error = (int)e;

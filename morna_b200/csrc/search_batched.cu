@@ -1095,16 +1095,7 @@ static int make_tmap(CUtensorMap *map, const void *ptr, uint64_t rows, uint64_t 
     return MORNA_OK;
 }
 
-static int sm_count_b() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
+static int sm_count_b() { return sm_count_current(); }
 
 constexpr int kCandCap = 4096, kFinCap = 1024, kPilotMax = kKthMax;
 constexpr int64_t kBatchedMaxRows = (int64_t)1 << 24;      // rows one call may score (ids are int32; TMA row coordinate)
@@ -1129,12 +1120,8 @@ static int g_rerank_pipe = 1;      // key 18: CTA-per-query re-rank with softwar
 static int launch_knn_gemm(const CUtensorMap &tmap_q, const CUtensorMap &tmap_s, const GemmParams &gp, cudaStream_t s,
                            const RerankParams *side = nullptr) {
     if (!g_gemm_pair) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            MORNA_CUDA_TRY(cudaFuncSetAttribute(knn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                gemm::SMEM_BYTES));
-            attr_set = true;
-        }
+        int rca = ensure_dynamic_smem((const void *)knn_gemm_kernel, gemm::SMEM_BYTES);
+        if (rca != MORNA_OK) return rca;
         int tiles = gp.m_blocks * gp.n_tiles;
         int grid = tiles < sm_count_b() ? tiles : sm_count_b();
         knn_gemm_kernel<<<grid, gemm::THREADS, gemm::SMEM_BYTES, s>>>(tmap_q, tmap_s, gp);
@@ -1144,7 +1131,8 @@ static int launch_knn_gemm(const CUtensorMap &tmap_q, const CUtensorMap &tmap_s,
     const int stages = g_gemm_stages == 4 ? 4 : 6;
     auto kern = stages == 4 ? knn_gemm2_kernel<4> : knn_gemm2_kernel<6>;
     const int smem = gemm2::smem_bytes(stages);
-    MORNA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int rca = ensure_dynamic_smem((const void *)kern, smem);
+    if (rca != MORNA_OK) return rca;
     int tiles = ((gp.m_blocks + 1) / 2) * gp.n_tiles;
     int pairs = sm_count_b() / 2;
     if (tiles < pairs) pairs = tiles;
@@ -1221,11 +1209,12 @@ extern "C" size_t morna_knn_batched_workspace_bytes(int64_t n, int64_t nq, int32
 
 // Scoring half of morna_knn_batched: fp16 tensor-core scores, thresholds and the final candidate
 // lists of every query, left in the workspace (tensor-core bound; touches HBM lightly).
-extern "C" int morna_knn_batched_score(const void *hs, int64_t ld_h, const float *rho_max, int64_t n, int32_t dim,
-                                       int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
-                                       uint8_t *overflow, int32_t *stats, void *workspace, size_t workspace_bytes,
-                                       void *const *phase_events, const morna_rerank_job *side_job, float *kth_bound,
-                                       void *stream) {
+// final_mode: 0 = final candidate lists, 1 = this rank's score bounds only (kth_bound), 2 = leave the first-pass lists
+static int score_impl(const void *hs, int64_t ld_h, const float *rho_max, int64_t n, int32_t dim,
+                      int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
+                      uint8_t *overflow, int32_t *stats, void *workspace, size_t workspace_bytes,
+                      void *const *phase_events, const morna_rerank_job *side_job, float *kth_bound, int final_mode,
+                      void *stream) {
     if (!hs || !rho_max || !queries || !overflow || !stats || n <= 0 || n > kBatchedMaxRows || nq <= 0 || dim <= 0 ||
         q_ld < dim || k <= 0 || k > kFinCap / 2 || ld_h != morna_tensor_operand_ld(dim))
         return MORNA_ERR_INVALID_ARGUMENT;
@@ -1293,9 +1282,9 @@ extern "C" int morna_knn_batched_score(const void *hs, int64_t ld_h, const float
     kp.pilot = pilot; kp.pilot_ld = w.pilot_ld; kp.eps = eps; kp.thr = thr; kp.cand_score = cand_score;
     kp.cand_id = cand_id; kp.cand_cnt = cand_cnt; kp.fin_id = fin_id; kp.fin_cnt = fin_cnt; kp.overflow = overflow;
     kp.stats = stats;
-    MORNA_CUDA_TRY(cudaFuncSetAttribute(kth_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKwSmem));
-    MORNA_CUDA_TRY(cudaFuncSetAttribute(kth_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKwSmem));
-    MORNA_CUDA_TRY(cudaFuncSetAttribute(kth_warp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKwSmem));
+    if ((rc = ensure_dynamic_smem((const void *)kth_warp_kernel<1>, kKwSmem)) != MORNA_OK) return rc;
+    if ((rc = ensure_dynamic_smem((const void *)kth_warp_kernel<0>, kKwSmem)) != MORNA_OK) return rc;
+    if ((rc = ensure_dynamic_smem((const void *)kth_warp_kernel<2>, kKwSmem)) != MORNA_OK) return rc;
     const unsigned kth_grid = (unsigned)((nq + kKwWarps - 1) / kKwWarps);
 
     rc = launch_gemm(0, (int32_t)w.n0, 0);                       // pilot block: dump scores
@@ -1326,15 +1315,110 @@ extern "C" int morna_knn_batched_score(const void *hs, int64_t ld_h, const float
         }
     }
     mark();                                                      // 4: filter GEMM(s)
-    if (kth_bound) {             // rows-sharded search: only this rank's bound; morna_knn_batched_finalize builds the lists
+    if (final_mode == 2) return MORNA_OK;
+    if (final_mode == 1) {       // rows-sharded search: only this rank's bounds; morna_knn_batched_finalize builds the lists
         kp.kth_bound = kth_bound;
-        MORNA_CUDA_TRY(cudaFuncSetAttribute(kth_warp_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKwSmem));
+        if ((rc = ensure_dynamic_smem((const void *)kth_warp_kernel<3>, kKwSmem)) != MORNA_OK) return rc;
         kth_warp_kernel<3><<<kth_grid, kKwWarps * 32, kKwSmem, s>>>(kp, (int)nq);
     } else {
         kth_warp_kernel<0><<<kth_grid, kKwWarps * 32, kKwSmem, s>>>(kp, (int)nq);
     }
     MORNA_LAUNCH_CHECK();
     mark();                                                      // 5: final candidate lists
+    return MORNA_OK;
+}
+
+extern "C" int morna_knn_batched_score(const void *hs, int64_t ld_h, const float *rho_max, int64_t n, int32_t dim,
+                                       int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
+                                       uint8_t *overflow, int32_t *stats, void *workspace, size_t workspace_bytes,
+                                       void *const *phase_events, const morna_rerank_job *side_job, float *kth_bound,
+                                       void *stream) {
+    return score_impl(hs, ld_h, rho_max, n, dim, id_base, queries, nq, q_ld, k, overflow, stats, workspace, workspace_bytes,
+                      phase_events, side_job, kth_bound, kth_bound ? 1 : 0, stream);
+}
+
+namespace morna {
+// which of the two first-pass list buffers is current after a scoring call: one swap per refinement between row blocks
+static int list_swaps(int64_t n, const BatchWs &w) {
+    int swaps = 0;
+    for (int64_t b0 = w.n0; b0 < n;) {
+        int64_t b1 = b0 == w.n0 ? (int64_t)(g_first_block > 0 ? g_first_block : g_block_rows) : b0 + g_block_rows;
+        if (b1 > n || b1 <= b0) b1 = n;
+        b0 = b1;
+        if (b0 < n) ++swaps;
+    }
+    return swaps;
+}
+
+// Approximate mode: the k best rows by fp16 tensor-core score, no FP64 re-rank.  One CTA per query sorts the
+// first-pass list (score descending, then id descending) in shared memory; distance = sqrt(2 - 2 score).
+constexpr int kApproxThreads = 512;
+__global__ void __launch_bounds__(kApproxThreads)
+approx_topk_kernel(const float *__restrict__ cand_score, const int32_t *__restrict__ cand_id, const int32_t *__restrict__ cand_cnt,
+                   int32_t cap, int32_t k, uint8_t *__restrict__ overflow, int32_t *__restrict__ stats,
+                   int32_t *__restrict__ out_ids, double *__restrict__ out_dist) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *ss = reinterpret_cast<float *>(smem_raw);          // [P]
+    int *si = reinterpret_cast<int *>(ss + cap);              // [P]
+    const int q = blockIdx.x, tid = threadIdx.x;
+    int32_t *oi = out_ids + (int64_t)q * k;
+    double *od = out_dist + (int64_t)q * k;
+    const int count = cand_cnt[q];
+    if (count > cap || overflow[q]) {                        // survivors were dropped (massive ties): the exact scan answers
+        if (tid == 0) { if (!overflow[q]) atomicAdd(stats + 0, 1); overflow[q] = 1; }
+        for (int i = tid; i < k; i += kApproxThreads) { oi[i] = -1; od[i] = INFINITY; }
+        return;
+    }
+    int P = 32;
+    while (P < count) P <<= 1;
+    for (int i = tid; i < P; i += kApproxThreads) {
+        const bool have = i < count;
+        ss[i] = have ? cand_score[(int64_t)q * cap + i] : -INFINITY;
+        si[i] = have ? cand_id[(int64_t)q * cap + i] : -1;
+    }
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = tid; i < (P >> 1); i += kApproxThreads) {
+                const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                const bool asc = (lo & size) == 0;
+                const float sl = ss[lo], sh = ss[hi];
+                const int il = si[lo], ih = si[hi];
+                const bool hi_first = sh > sl || (sh == sl && ih > il);      // larger score first, then larger id
+                const bool lo_first = sl > sh || (sl == sh && il > ih);
+                if (asc ? hi_first : lo_first) { ss[lo] = sh; ss[hi] = sl; si[lo] = ih; si[hi] = il; }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < k; i += kApproxThreads) {
+        const bool ok = i < count && si[i] >= 0;
+        oi[i] = ok ? si[i] : -1;
+        double d = 2.0 - 2.0 * (double)ss[i < P ? i : 0];
+        if (d < 0.0) d = 0.0;
+        od[i] = ok ? sqrt(d) : INFINITY;
+    }
+    if (tid == 0) atomicAdd(stats + 1, count);
+}
+}  // namespace morna
+
+extern "C" int morna_knn_batched_approx(const void *hs, int64_t ld_h, const float *rho_max, int64_t n, int32_t dim,
+                                        int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
+                                        int32_t *out_ids, double *out_dist, uint8_t *overflow, int32_t *stats,
+                                        void *workspace, size_t workspace_bytes, void *stream) {
+    if (!out_ids || !out_dist) return MORNA_ERR_INVALID_ARGUMENT;
+    int rc = score_impl(hs, ld_h, rho_max, n, dim, id_base, queries, nq, q_ld, k, overflow, stats, workspace, workspace_bytes,
+                        nullptr, nullptr, nullptr, 2, stream);
+    if (rc != MORNA_OK) return rc;
+    BatchWs w = batch_ws_layout(n, nq, ld_h);
+    unsigned char *ws = (unsigned char *)workspace;
+    const int swaps = list_swaps(n, w);
+    const float *cs = (const float *)(ws + ((swaps & 1) ? w.cand2_score : w.cand_score));
+    const int32_t *ci = (const int32_t *)(ws + ((swaps & 1) ? w.cand2_id : w.cand_id));
+    const size_t smem = (size_t)kCandCap * (sizeof(float) + sizeof(int));
+    morna::approx_topk_kernel<<<(unsigned)nq, morna::kApproxThreads, smem, (cudaStream_t)stream>>>(
+        cs, ci, (const int32_t *)(ws + w.cand_cnt), kCandCap, k, overflow, stats, out_ids, out_dist);
+    MORNA_LAUNCH_CHECK();
     return MORNA_OK;
 }
 
@@ -1382,20 +1466,14 @@ extern "C" int morna_knn_batched_finalize(int64_t n, int64_t nq, int32_t dim, in
     if (!workspace || workspace_bytes < w.total) return MORNA_ERR_WORKSPACE_TOO_SMALL;
     unsigned char *ws = (unsigned char *)workspace;
     // which of the two list buffers is current: one swap per refinement between row blocks (same walk as the scoring call)
-    int swaps = 0;
-    for (int64_t b0 = w.n0; b0 < n;) {
-        int64_t b1 = b0 == w.n0 ? (int64_t)(g_first_block > 0 ? g_first_block : g_block_rows) : b0 + g_block_rows;
-        if (b1 > n || b1 <= b0) b1 = n;
-        b0 = b1;
-        if (b0 < n) ++swaps;
-    }
+    const int swaps = list_swaps(n, w);
     KthParams kp{};
     kp.k = k; kp.n0 = (int32_t)w.n0; kp.cap = kCandCap; kp.fcap = kFinCap; kp.eps = (const float *)(ws + w.eps);
     kp.cand_score = (float *)(ws + ((swaps & 1) ? w.cand2_score : w.cand_score));
     kp.cand_id = (int32_t *)(ws + ((swaps & 1) ? w.cand2_id : w.cand_id));
     kp.cand_cnt = (int32_t *)(ws + w.cand_cnt); kp.fin_id = (int32_t *)(ws + w.fin_id); kp.fin_cnt = (int32_t *)(ws + w.fin_cnt);
     kp.overflow = overflow; kp.stats = stats; kp.kth_bound = const_cast<float *>(kth_bound);
-    MORNA_CUDA_TRY(cudaFuncSetAttribute(kth_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKwSmem));
+    { int rca = ensure_dynamic_smem((const void *)kth_warp_kernel<4>, kKwSmem); if (rca != MORNA_OK) return rca; }
     kth_warp_kernel<4><<<(unsigned)((nq + kKwWarps - 1) / kKwWarps), kKwWarps * 32, kKwSmem, (cudaStream_t)stream>>>(kp, (int)nq);
     MORNA_LAUNCH_CHECK();
     return MORNA_OK;
@@ -1478,7 +1556,7 @@ extern "C" int morna_knn_batched_rerank(const float *vectors, const double *pp, 
         auto kern = g_rerank_rows == 2 ? rerank_dist_kernel<2> : g_rerank_rows == 4 ? rerank_dist_kernel<4> : rerank_dist_kernel<8>;
         if (g_rerank_pipe) kern = g_rerank_rows == 4 ? rerank_dist_kernel<4, true> : g_rerank_rows == 16 ? rerank_dist_kernel<16, true>
                                                                                                         : rerank_dist_kernel<8, true>;
-        MORNA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
+        if ((rc = ensure_dynamic_smem((const void *)kern, rr_smem)) != MORNA_OK) return rc;
         int per_sm = 0;
         MORNA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRrThreads, rr_smem));
         if (per_sm < 1) per_sm = 1;

@@ -238,16 +238,7 @@ select_topk_kernel(const double *__restrict__ keys, const int32_t *__restrict__ 
     }
 }
 
-static int sm_count_cached() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
+static int sm_count_cached() { return sm_count_current(); }
 
 static size_t select_level_entries(int64_t n, int32_t k) {
     int64_t chunks = (n + kSelChunk - 1) / kSelChunk;
@@ -342,8 +333,10 @@ static int launch_distances(const float *vectors, const double *pp, int64_t n, i
     size_t smem = (size_t)QB * ld * sizeof(double);
     if (smem > 200 * 1024) return MORNA_ERR_INVALID_ARGUMENT;
     auto kern = angular_distances_kernel<QB>;
-    if (smem > 48 * 1024)
-        MORNA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) {
+        int rca = ensure_dynamic_smem((const void *)kern, smem);
+        if (rca != MORNA_OK) return rca;
+    }
     int per_sm = (int)((220 * 1024) / (smem + 1024));
     if (per_sm > 8) per_sm = 8;
     if (per_sm < 1) per_sm = 1;
@@ -452,11 +445,7 @@ extern "C" int morna_merge_sorted_topk(const double *dists, const int32_t *ids, 
     if (nq == 0) return MORNA_OK;
     const size_t smem = (size_t)n_lists * k_in * (sizeof(double) + sizeof(int32_t));
     if (smem > 200 * 1024 || nq > 0x7fffffff) return MORNA_ERR_INVALID_ARGUMENT;
-    static size_t attr = 0;
-    if (smem > attr) {
-        MORNA_CUDA_TRY(cudaFuncSetAttribute(morna::merge_sorted_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
+    { int rca = ensure_dynamic_smem((const void *)morna::merge_sorted_topk_kernel, smem); if (rca != MORNA_OK) return rca; }
     morna::merge_sorted_topk_kernel<<<(unsigned)nq, morna::kMergeThreads, smem, (cudaStream_t)stream>>>(
         dists, ids, n_lists, nq, k_in, k_out, out_ids, out_dist);
     MORNA_LAUNCH_CHECK();
@@ -473,11 +462,7 @@ extern "C" int morna_select_topk(const double *keys, const int32_t *ids, int64_t
     if (workspace_bytes < morna_select_topk_workspace_bytes(n, nq, k)) return MORNA_ERR_WORKSPACE_TOO_SMALL;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t smem = (size_t)kSelChunk * (sizeof(double) + sizeof(int));
-    static bool attr_set = false;
-    if (!attr_set) {
-        MORNA_CUDA_TRY(cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    { int rca = ensure_dynamic_smem((const void *)select_topk_kernel, smem); if (rca != MORNA_OK) return rca; }
     size_t entries = select_level_entries(n, k) * (size_t)nq;
     unsigned char *ws = (unsigned char *)workspace;
     double *bufd[2];

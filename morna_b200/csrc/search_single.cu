@@ -423,16 +423,7 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
 static int g_single_rows = 0;     // morna_debug_set_tuning key 3: rows per warp pass (0 = automatic)
 void set_single_tma(int v) { g_single_rows = v; }
 
-static int sm_count_s() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
+static int sm_count_s() { return sm_count_current(); }
 
 struct SingleLayout { size_t ctl, hist, lists, dist, sel, total; };
 static SingleLayout single_layout(int64_t n) {
@@ -452,11 +443,7 @@ template <int R, int U>
 static int launch_scan64(unsigned grid, size_t smem, cudaStream_t s, const float *vectors, const double *pp, int64_t n,
                          int64_t ld, int32_t dim, int32_t id_base, const double *query, int32_t k, int64_t rows_per_warp,
                          double *dist, float *sel, unsigned int *hist, int32_t *lists, SingleWs *ctl, int32_t *out_ids, double *out_dist, int32_t *fallback) {
-    static size_t attr = 0;             // shared-memory opt-in is sticky per function (static smem counts too)
-    if (smem > attr) {
-        MORNA_CUDA_TRY(cudaFuncSetAttribute(scan64_select_kernel<R, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
+    { int rca = ensure_dynamic_smem((const void *)scan64_select_kernel<R, U>, smem); if (rca != MORNA_OK) return rca; }
     scan64_select_kernel<R, U><<<grid, kS1Threads, smem, s>>>(vectors, pp, n, ld, dim, id_base, query, k, rows_per_warp,
                                                               dist, sel, hist, lists, ctl, out_ids, out_dist, fallback);
     MORNA_LAUNCH_CHECK();

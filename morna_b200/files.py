@@ -88,3 +88,37 @@ def read_annoy_item_vectors(path, n_items, dim):
         raise ValueError("%s is too small for %d items of dimension %d" % (path, n_items, dim))
     rows = np.lib.stride_tricks.as_strided(raw[12:], shape=(n_items, 4 * dim), strides=(stride, 1))
     return np.ascontiguousarray(rows).view("<f4").reshape(n_items, dim)
+
+
+def write_meta(basename, metafile):
+    """basename.meta.mor, the sqlite table the reference's search joins results against (morna.py:494-520): one row
+    per line of `metafile` -- first whitespace-separated column the sample id, the rest of the line (newline included,
+    as the reference keeps it) the keywords.  An existing table is dropped first."""
+    import sqlite3
+    conn = sqlite3.connect(basename + ".meta.mor")
+    cursor = conn.cursor()
+    cursor.execute("SELECT name FROM sqlite_master WHERE type='table' AND name='metadata'")
+    if cursor.fetchone():
+        cursor.execute("DROP TABLE metadata")
+    cursor.execute("CREATE TABLE metadata (sample_id real, keywords text)")
+    with open(metafile) as fh:
+        for line in fh:
+            parts = line.split(None, 1)
+            if len(parts) < 2:
+                raise IndexError("list index out of range")           # the reference indexes [1] of a one-column line
+            cursor.execute("INSERT INTO metadata VALUES (?,?)", (parts[0], parts[1]))
+    conn.commit()
+    conn.close()
+
+
+def read_meta(basename, sample_ids):
+    """The join of morna.py:666-676: for each sample id the first matching row's (keywords,) tuple, or None."""
+    import sqlite3
+    conn = sqlite3.connect(basename + ".meta.mor")
+    cursor = conn.cursor()
+    out = []
+    for sample_id in sample_ids:
+        cursor.execute("SELECT keywords FROM metadata WHERE sample_id=?", (str(sample_id),))
+        out.append(cursor.fetchone())
+    conn.close()
+    return out

@@ -228,6 +228,8 @@ class MornaIndex(object):
         files.write_stats(basename, self.sample_count, self.new_internal_id, self.dim)
         files.write_freq(basename, self.sample_frequencies)
         files.write_map(basename, self.internal_id_map)
+        if self.metafile:                                  # morna.py:494-520
+            files.write_meta(basename, self.metafile)
 
 
 def go_index(intropolis, basename, features, n_trees, sample_count, sample_threshold, buffer_size,

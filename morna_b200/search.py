@@ -479,10 +479,48 @@ class MornaSearch(object):
             results += (self._metadata(results[0]),)
         return results
 
-    # The reference's default mode asks Annoy for approximate neighbours
-    # (morna.py:632-678).  The forest is out of scope; exact search answers instead.
+    # ------------------------------------------------------------------ approximate mode
+    def approx_search_device(self, queries, k):
+        """The k best rows by fp16 tensor-core score, no exact re-rank (morna_knn_batched_approx): the approximate mode
+        that stands where the reference asks Annoy (morna.py:632-678).  Same contract as batched_search_device; queries
+        whose lists overflow, tiny shards and sparse indexes are answered exactly."""
+        self.enable_tensor_path()
+        assert queries.is_cuda and queries.dtype == torch.float64 and queries.dim() == 2 and queries.shape[1] == self.dim
+        queries = queries.contiguous()
+        nq, dev = queries.shape[0], self.device
+        n = self.row_hi - self.row_lo
+        if n == 0 or nq == 0 or k > 512 or k <= 0 or k > n or n > self.BATCH_BLOCK_ROWS or (self.csr is not None and self.sparse_exact):
+            return self.exact_search_device(queries, k)
+        with torch.cuda.device(dev):
+            out_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+            out_d = torch.empty((nq, k), dtype=torch.float64, device=dev)
+            overflow = torch.empty(nq, dtype=torch.uint8, device=dev)
+            stats = torch.empty(4, dtype=torch.int32, device=dev)
+            need = self.lib.morna_knn_batched_workspace_bytes(n, nq, self.dim, k)
+            sid = torch.cuda.current_stream(dev).cuda_stream
+            ws = self._bws.get(sid)
+            if ws is None or ws.numel() < need:
+                ws = self._bws[sid] = _lib.workspace(need, dev)
+            _lib.check(self.lib.morna_knn_batched_approx(
+                _lib.dev_ptr(self.hs), self.ld_h, _lib.dev_ptr(self.rho_max), n, self.dim, self.row_lo, _lib.ptr(queries), nq,
+                self.dim, k, _lib.dev_ptr(out_ids), _lib.dev_ptr(out_d), _lib.dev_ptr(overflow), _lib.dev_ptr(stats),
+                _lib.dev_ptr(ws), ws.numel(), _lib.stream_ptr()), "morna_knn_batched_approx")
+        return self._batched_finish([(0, n, out_ids, out_d, overflow, stats)], queries, k)
+
     def search_nn(self, num_neighbors, search_k=None, include_distances=True, meta_db=False):
-        return self.exact_search_nn(num_neighbors, include_distances, meta_db)
+        """morna.py:632-678 for the current ``query_sample``: the reference's default (approximate) mode.  Annoy's
+        forest is not rebuilt here; the approximate answer is the tensor-core pass without the exact re-rank
+        (``search_k`` has no counterpart and is ignored).  ``exact_search_nn`` (-e) is the exact mode."""
+        q = torch.tensor(self.query_sample, dtype=torch.float64)[None, :].to(self.device)
+        ids, d = self.approx_search_device(q, num_neighbors)
+        ids, d = ids.cpu().numpy(), d.cpu().numpy()
+        keep = ids[0] >= 0
+        results = (ids[0][keep].tolist(),)
+        if include_distances:
+            results += (d[0][keep].tolist(),)
+        if meta_db:
+            results += (self._metadata(results[0]),)
+        return results
 
     def search_member_n(self, query_id, num_neighbors, search_k=None, include_distances=True,
                         meta_db=False, out=None):
@@ -504,15 +542,8 @@ class MornaSearch(object):
         return self.exact_search_nn(num_neighbors, include_distances, meta_db)
 
     def _metadata(self, internal_ids):
-        import sqlite3
-        conn = sqlite3.connect(self.basename + ".meta.mor")
-        cur = conn.cursor()
-        out = []
-        for iid in internal_ids:
-            cur.execute("SELECT keywords FROM metadata WHERE sample_id=?", (str(self.inverse_lookup(iid)),))
-            out.append(cur.fetchone())
-        conn.close()
-        return out
+        """morna.py:666-676: keywords of every result's sample id from basename.meta.mor."""
+        return files.read_meta(self.basename, [self.inverse_lookup(iid) for iid in internal_ids])
 
 
 class _PipeSlot(object):

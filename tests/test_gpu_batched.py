@@ -407,3 +407,36 @@ def test_sparse_exact_path_matches_dense_kernels_bit_for_bit(n, d, max_nnz):
     s_ids, s_d = srch.exact_search_device(q, 5)
     d_ids, d_d = dense.exact_search_device(q, 5, allow_single=False)
     assert torch.equal(s_ids, d_ids)
+
+
+def test_approximate_mode_recall_and_distances():
+    """MornaSearch.approx_search_device / search_nn: the tensor-core pass without the exact re-rank.  Recall@k against the
+    exact answer stays high (ids differ only where cosines are closer than the fp16 error), distances are within the
+    fp16 error of the true ones, well-separated data is answered exactly."""
+    n, d, nq, k = 20000, 1000, 500, 50
+    S = __import__("morna_b200.synth", fromlist=["x"]).gauss(n, d, "cuda", seed=21)
+    srch = make_search(S)
+    from morna_b200 import synth
+    q, rows = synth.queries(S, nq, noise=0.05)
+    e_ids, e_d = srch.batched_search_device(q, k)
+    a_ids, a_d = srch.approx_search_device(q, k)
+    hits = sum(len(set(a_ids[j].tolist()) & set(e_ids[j].tolist())) for j in range(nq))
+    recall = hits / float(nq * k)
+    assert recall >= 0.95, recall
+    S64 = S.double()
+    cos = (q @ S64.t()) / (q.norm(dim=1, keepdim=True) * S64.norm(dim=1)[None, :])
+    true_d = (2 - 2 * cos).clamp_min(0).sqrt()
+    err = (a_d - torch.gather(true_d, 1, a_ids.long())).abs().max()
+    assert float(err) < 2e-3
+    assert bool((a_d[:, 1:] >= a_d[:, :-1]).all())
+    print("approximate mode: recall@%d = %.4f, max distance error %.2e" % (k, recall, float(err)))
+    T = synth.tissue(8000, 600, "cuda", seed=5)
+    ts = make_search(T)
+    tq, _ = synth.queries(T, 200, noise=0.05)
+    ta, _ = ts.approx_search_device(tq, 5)
+    te, _ = ts.batched_search_device(tq, 5)
+    assert float((ta == te).float().mean()) > 0.97
+    # search_nn on the current query sample (what `morna.py search` without -e calls)
+    srch.query_sample = q[0].cpu().tolist()
+    ids, dists = srch.search_nn(k)
+    assert ids == a_ids[0].tolist() and len(dists) == k

@@ -336,6 +336,19 @@ def test_cli_index_then_exact_search_of_in_index_sample(tmp_path):
     check_topk(true_d, [int(r[1]) for r in got], [float(r[2]) for r in got], tol=1e-7, dist_tol=1e-5)
     with pytest.raises(ValueError):
         cli.main(["search", "-x", base, "-q", "999999", "-e"], stdout=io.StringIO())
+    # -m: index with a metadata file, search joins every result's sample id against basename.meta.mor (morna.py:494-520, 666-676)
+    meta = tmp_path / "meta.tsv"
+    inv = {v: k for k, v in files.read_map(base).items()}
+    top = [inv[i] for i in exp["queries"][0]["ids"][:3]]
+    meta.write_text("".join("%d\ttissue_%d blood\n" % (sid, sid) for sid in top[:2]) + "12 the query itself\n")
+    assert cli.main(["index", "--intropolis", os.path.join(GOLDEN, "tiny_intropolis.tsv"), "-x", base, "-m", str(meta)],
+                    stdout=io.StringIO()) == 0
+    out = io.StringIO()
+    assert cli.main(["search", "-x", base, "-q", "12", "-e", "-m", "-r", "3"], stdout=out) == 0
+    rows = [l.split("\t") for l in out.getvalue().splitlines()[2:]]
+    assert [int(r[1]) for r in rows] == exp["queries"][0]["ids"][:3]
+    assert rows[0][2] == "(u'tissue_%d blood\\n',)" % top[0] and rows[1][2] == "(u'tissue_%d blood\\n',)" % top[1]
+    assert rows[2][2] == "None"                                      # no metadata line for that sample
 
 
 # ------------------------------------------------------------------ single query, fused FP64 scan + select

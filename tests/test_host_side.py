@@ -217,3 +217,21 @@ def test_native_tokenizer_random_rows_and_thread_counts():
         assert _native_rows(text, n_threads) == want
     blocks = list(parse.read_blocks(io.BytesIO(text), block_bytes=4096))
     assert b"".join(blocks) == text and all(b.endswith(b"\n") for b in blocks)
+
+
+def test_metadata_db_round_trip(tmp_path):
+    """basename.meta.mor as morna.py:494-520 writes it and :666-676 reads it: numeric ids match through sqlite's REAL
+    affinity, keywords keep their newline, a second index run replaces the table, Python 2 prints the row as (u'..',)."""
+    from morna_b200 import cli, files
+    base = str(tmp_path / "idx")
+    meta = tmp_path / "meta.txt"
+    meta.write_text("12 liver  adult\n21504\tblood\n7 x\n")
+    files.write_meta(base, str(meta))
+    assert files.read_meta(base, [12, 21504, 99, 7]) == [("liver  adult\n",), ("blood\n",), None, ("x\n",)]
+    meta.write_text("5 only\n")
+    files.write_meta(base, str(meta))
+    assert files.read_meta(base, [12, 5]) == [None, ("only\n",)]
+    assert cli.py2_str(("blood\n",)) == "(u'blood\\n',)" and cli.py2_str(None) == "None"
+    meta.write_text("13\n")
+    with pytest.raises(IndexError):
+        files.write_meta(base, str(meta))
