@@ -702,7 +702,7 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     volatile uint32_t *tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     int *helper_lists = reinterpret_cast<int *>(smem_raw + (bars + 256u - smem_u32(smem_raw)));     // [HELPER_WARPS][1024]
-    volatile int *helper_stop = helper_lists + HELPER_WARPS * 1024;
+    volatile int *helper_stop = helper_lists + (blockDim.x > THREADS ? HELPER_WARPS * 1024 : 0);      // (no lists without helpers)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -1115,6 +1115,9 @@ static int g_rerank_subs = 0;      // key 16: items per query of the unsplit war
 static int g_side_job = 0;         // key 17: 1 = side jobs on: helper warps in the GEMM kernel re-rank the previous batch (measured slower:
                                    // the GEMM's TMA stream and the helpers' gathers queue behind each other)
 static int g_rerank_pipe = 1;      // key 18: CTA-per-query re-rank with software-pipelined row loads
+static int g_carveout_hint = 0;    // key 19: ask for the maximum shared-memory carve-out on the batched path's kernels (co-residency across streams)
+static int g_rerank_oneshot = 1;   // key 20: CTA-per-query re-rank launched as one CTA per item (default; 0 = persistent grid): its CTAs retire one by
+                                   // one, so the next batch's first kernels start under its tail (1.875 -> 1.834 ms per headline batch)
 
 
 static int launch_knn_gemm(const CUtensorMap &tmap_q, const CUtensorMap &tmap_s, const GemmParams &gp, cudaStream_t s,
@@ -1138,7 +1141,11 @@ static int launch_knn_gemm(const CUtensorMap &tmap_q, const CUtensorMap &tmap_s,
     if (tiles < pairs) pairs = tiles;
     RerankParams rr{};
     if (side) rr = *side;
-    kern<<<2 * pairs, gemm2::THREADS_ALL, smem, s>>>(tmap_q, tmap_s, gp, rr);
+    if (g_carveout_hint) cudaFuncSetAttribute((const void *)kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    // without a side job the helper warps are not launched at all (192 threads, no candidate-list shared memory)
+    const int threads = side ? gemm2::THREADS_ALL : gemm2::THREADS;
+    const int smem_launch = side ? smem : smem - gemm2::HELPER_BYTES + 16;
+    kern<<<2 * pairs, threads, smem_launch, s>>>(tmap_q, tmap_s, gp, rr);
     MORNA_LAUNCH_CHECK();
     return MORNA_OK;
 }
@@ -1563,7 +1570,8 @@ extern "C" int morna_knn_batched_rerank(const float *vectors, const double *pp, 
         if (g_rerank_ctas_per_sm > 0 && per_sm > g_rerank_ctas_per_sm) per_sm = g_rerank_ctas_per_sm;
         const int64_t items = (int64_t)nq * rp.phases;
         int64_t rr_grid = (int64_t)per_sm * sm_count_b();
-        if (rr_grid > items) rr_grid = items;
+        if (rr_grid > items || g_rerank_oneshot) rr_grid = items;
+        if (g_carveout_hint) cudaFuncSetAttribute((const void *)kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         kern<<<(unsigned)rr_grid, kRrThreads, rr_smem, s>>>(rp);
         MORNA_LAUNCH_CHECK();
     }
@@ -1644,6 +1652,8 @@ extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
     else if (key == 16) g_rerank_subs = value;
     else if (key == 17) g_side_job = value;
     else if (key == 18) g_rerank_pipe = value;
+    else if (key == 19) g_carveout_hint = value;
+    else if (key == 20) g_rerank_oneshot = value;
 
     else return MORNA_ERR_INVALID_ARGUMENT;
     return MORNA_OK;
