@@ -205,12 +205,18 @@ int morna_knn_single(const float *vectors, const double *pp, int64_t n, int32_t 
  * and tie): the rows are given in CSR form and a (query, row) distance costs nnz(row) multiply-adds.  The non-zero
  * terms are added in the dense kernels' order, so ids and distances are bit-identical to morna_knn_exact.
  *   row_off [dev] int64[n+1]   cols [dev] int32[nnz] ascending within a row   vals [dev] float32[nnz] (non-zero)
+ *   plan    [dev] int32[n]     summation plan of every row: bit 30 set = no plan (any row may say so); otherwise, for a
+ *                              row of nnz <= 3 entries, bits 8..12 = nnz and bits 2e..2e+1 = the accumulator (0, 1, 2) entry e
+ *                              adds into, the result being (a0 + a1) + a2.  Entries whose summation lane (col/4)%32 is
+ *                              equal share an accumulator; of three distinct lanes the two with the largest
+ *                              lowbit(lane_i xor lane_j) take accumulators 0 and 1.  (MornaSearch._build_csr makes it.)
  *   pp      [dev] double[n] squared row norms (morna_row_norms of the dense rows) */
 int32_t morna_sparse_max_nnz(void);
 size_t morna_knn_exact_sparse_workspace_bytes(int64_t n, int64_t nq, int32_t k);
-int morna_knn_exact_sparse(const int64_t *row_off, const int32_t *cols, const float *vals, const double *pp, int64_t n,
-                           int32_t dim, int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
-                           int32_t *out_ids, double *out_dist, void *workspace, size_t workspace_bytes, void *stream);
+int morna_knn_exact_sparse(const int64_t *row_off, const int32_t *cols, const float *vals, const int32_t *plan,
+                           const double *pp, int64_t n, int32_t dim, int32_t id_base, const double *queries, int64_t nq,
+                           int64_t q_ld, int32_t k, int32_t *out_ids, double *out_dist, void *workspace,
+                           size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------ batched search (tensor cores) */
 

@@ -61,7 +61,7 @@ _SIGNATURES = {
                                        _c_i32, _c_vp, _c_vp, _c_vp, _c_sz, _c_vp]),
     "morna_sparse_max_nnz": (_c_i32, []),
     "morna_knn_exact_sparse_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_i32]),
-    "morna_knn_exact_sparse": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp, _c_i64, _c_i64, _c_i32,
+    "morna_knn_exact_sparse": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp, _c_i64, _c_i64, _c_i32,
                                               _c_vp, _c_vp, _c_vp, _c_sz, _c_vp]),
     "morna_knn_single_workspace_bytes": (_c_sz, [_c_i64]),
     "morna_knn_single_workspace_init": (ctypes.c_int, [_c_vp, _c_sz, _c_vp]),

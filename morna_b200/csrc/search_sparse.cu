@@ -36,16 +36,10 @@ query_norms_kernel(const double *__restrict__ queries, int64_t nq, int64_t q_ld,
     if (lane == 0) qq[q] = acc;
 }
 
-// thread = (row, query): the row's non-zeros against the query, summed in the canonical order
-__global__ void __launch_bounds__(kSparseThreads)
-sparse_distances_kernel(const int64_t *__restrict__ row_off, const int32_t *__restrict__ cols, const float *__restrict__ vals,
-                        const double *__restrict__ pp, int64_t n, const double *__restrict__ queries, int64_t q_ld,
-                        const double *__restrict__ qq, double *__restrict__ dist, int64_t dist_ld) {
-    const int64_t row = (int64_t)blockIdx.x * kSparseThreads + threadIdx.x;
-    const int64_t q = blockIdx.y;
-    if (row >= n) return;
-    const double *qv = queries + q * q_ld;
-    const int64_t e0 = row_off[row], e1 = row_off[row + 1];
+// The canonical sum of a row with more than three non-zeros: per-lane partial sums by ascending column, then the
+// xor-butterfly emulated on the lanes that hold anything (rare rows; kept out of line so the common path stays lean).
+__device__ __noinline__ double sparse_dot_generic(const int32_t *__restrict__ cols, const float *__restrict__ vals, int64_t e0,
+                                                  int64_t e1, const double *__restrict__ qv) {
     int lane_of[kSparseMaxNnz];
     double sum_of[kSparseMaxNnz];
     int m = 0;
@@ -73,8 +67,60 @@ sparse_distances_kernel(const int64_t *__restrict__ row_off, const int32_t *__re
             lane_of[i] &= ~bit;
         }
     }
-    const double pq = m > 0 ? sum_of[0] : 0.0;
-    dist[q * dist_ld + row] = angular_from_sums(pp[row], qq[q], pq);
+    return m > 0 ? sum_of[0] : 0.0;
+}
+
+constexpr int kSparseQT = 4;             // queries per thread: the row's entries are loaded once for all of them
+
+// thread = (row, kSparseQT queries).  Rows with at most three non-zeros -- the common case -- follow a per-row PLAN made
+// at index load (MornaSearch._build_csr): every entry adds into one of three accumulators (entries of one summation lane
+// share an accumulator, in ascending column order) and the result is (a0 + a1) + a2, the order in which the butterfly
+// meets these lanes (the two lanes whose indices differ in the highest "lowest differing bit" meet first).  plan bits:
+// 2e..2e+1 = accumulator of entry e, 8..12 = nnz, 30 = generic row.
+__global__ void __launch_bounds__(kSparseThreads)
+sparse_distances_kernel(const int64_t *__restrict__ row_off, const int32_t *__restrict__ cols, const float *__restrict__ vals,
+                        const int32_t *__restrict__ plan, const double *__restrict__ pp, int64_t n,
+                        const double *__restrict__ queries, int64_t nq, int64_t q_ld, const double *__restrict__ qq,
+                        double *__restrict__ dist, int64_t dist_ld) {
+    const int64_t row = (int64_t)blockIdx.x * kSparseThreads + threadIdx.x;
+    const int64_t q0 = (int64_t)blockIdx.y * kSparseQT;
+    if (row >= n) return;
+    const int pl = plan[row];
+    const int64_t e0 = row_off[row];
+    const double ppr = pp[row];
+    if (pl & (1 << 30)) {
+        const int64_t e1 = row_off[row + 1];
+        for (int t = 0; t < kSparseQT && q0 + t < nq; ++t) {
+            const double pq = sparse_dot_generic(cols, vals, e0, e1, queries + (q0 + t) * q_ld);
+            dist[(q0 + t) * dist_ld + row] = angular_from_sums(ppr, qq[q0 + t], pq);
+        }
+        return;
+    }
+    const int nnz = (pl >> 8) & 31;
+    int c[3] = {0, 0, 0};
+    double v[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+        if (e < nnz) { c[e] = cols[e0 + e]; v[e] = (double)vals[e0 + e]; }
+#pragma unroll
+    for (int t = 0; t < kSparseQT; ++t) {
+        if (q0 + t >= nq) break;
+        const double *qv = queries + (q0 + t) * q_ld;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            if (e < nnz) {
+                const double qe = __ldg(qv + c[e]);
+                const int tgt = (pl >> (2 * e)) & 3;
+                if (tgt == 0) a0 = fma(v[e], qe, a0);
+                else if (tgt == 1) a1 = fma(v[e], qe, a1);
+                else a2 = fma(v[e], qe, a2);
+            }
+        }
+        const double pq = (a0 + a1) + a2;
+        // pq == 0: 2 - 2*0/x = 2 whatever the norms are -- skip the division and the first square root
+        dist[(q0 + t) * dist_ld + row] = pq == 0.0 ? sqrt(2.0) : angular_from_sums(ppr, qq[q0 + t], pq);
+    }
 }
 
 // ---- exact top-k under massive ties ------------------------------------------------------------------------------
@@ -107,25 +153,45 @@ select_radix_kernel(const double *__restrict__ dist, int64_t n, int64_t dist_ld,
         for (int i = tid; i < k; i += kRsThreads) { oi[i] = -1; od[i] = INFINITY; }
         return;
     }
+    __shared__ unsigned long long s_and, s_or;
+    __shared__ int s_bin_count;
     if (tid == 0) { s_prefix = 0ull; s_need = kk; s_count = 0; s_ties = 0; }
     unsigned long long mask = 0ull;
+    constexpr int kUnroll = 4;                                         // independent loads in flight per thread (the passes are L2-latency bound)
     for (int shift = 64 - kRsBits; ; shift -= kRsBits) {               // digits at bits 53, 42, 31, 20, 9 and the last 9 bits
         const int width = shift >= 0 ? kRsBits : kRsBits + shift;
         const int sh = shift >= 0 ? shift : 0;
         const unsigned int bins = 1u << width;
         for (int b = tid; b < kRsBins; b += kRsThreads) hist[b] = 0u;
+        if (tid == 0) { s_and = ~0ull; s_or = 0ull; }
         __syncthreads();
         const unsigned long long prefix = s_prefix;
-        for (int64_t i0 = 0; i0 < n; i0 += kRsThreads) {
-            const int64_t i = i0 + tid;
-            unsigned int digit = 0xffffffffu;
-            if (i < n) {
-                const unsigned long long key = (unsigned long long)__double_as_longlong(row[i]);
-                if ((key & mask) == prefix) digit = (unsigned int)(key >> sh) & (bins - 1u);
+        unsigned long long my_and = ~0ull, my_or = 0ull;
+        for (int64_t i0 = 0; i0 < n; i0 += kUnroll * kRsThreads) {
+            unsigned long long key[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int64_t i = i0 + u * kRsThreads + tid;
+                key[u] = i < n ? (unsigned long long)__double_as_longlong(row[i]) : ~0ull;
             }
-            const unsigned int peers = __match_any_sync(kFull, digit);
-            if (digit != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int64_t i = i0 + u * kRsThreads + tid;
+                unsigned int digit = 0xffffffffu;
+                if (i < n && (key[u] & mask) == prefix) {
+                    digit = (unsigned int)(key[u] >> sh) & (bins - 1u);
+                    my_and &= key[u]; my_or |= key[u];
+                }
+                const unsigned int peers = __match_any_sync(kFull, digit);
+                if (digit != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
+            }
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            my_and &= __shfl_xor_sync(kFull, my_and, o);
+            my_or |= __shfl_xor_sync(kFull, my_or, o);
+        }
+        if (lane == 0) { atomicAnd(&s_and, my_and); atomicOr(&s_or, my_or); }
         __syncthreads();
         // the bin in which the cumulative count reaches s_need: every thread owns two consecutive bins
         const unsigned int h0 = hist[2 * tid], h1 = hist[2 * tid + 1];
@@ -140,18 +206,28 @@ select_radix_kernel(const double *__restrict__ dist, int64_t n, int64_t dist_ld,
         unsigned int before = incl - (h0 + h1);
         for (int w = 0; w < warp; ++w) before += warp_tot[w];
         const unsigned int need = (unsigned int)s_need;
-        __syncthreads();                                               // everyone has read s_need / warp_tot
+        const bool all_equal = s_and == s_or;                          // every key still matching the prefix is the same key
+        const unsigned long long the_key = s_or;
+        __syncthreads();                                               // everyone has read s_need / warp_tot / s_and / s_or
+        if (all_equal) {                                               // thousands of exact ties: no need to walk the lower digits
+            if (tid == 0) s_prefix = the_key;                          // (s_need stays: that many of the tied rows belong to the answer)
+            mask = ~0ull;
+            __syncthreads();
+            break;
+        }
         if (before < need && need <= before + h0 + h1) {
             const int bin = need <= before + h0 ? 2 * tid : 2 * tid + 1;
             s_need = (int)(need - (bin == 2 * tid ? before : before + h0));
             s_prefix = prefix | ((unsigned long long)bin << sh);
+            s_bin_count = (int)(bin == 2 * tid ? h0 : h1);
         }
         mask |= (unsigned long long)(bins - 1u) << sh;
         __syncthreads();
-        if (shift <= 0) break;
+        if (shift <= 0 || s_need == s_bin_count) break;                // every key with this prefix is wanted: lower digits do not matter
     }
-    const unsigned long long key_k = s_prefix;                         // the kk-th smallest key
-    const int quota = s_need;                                          // how many of the rows tied with it belong to the answer
+    // keys are compared under `mask` from here on: either all 64 bits, or the prefix of a bin that is wanted whole
+    const unsigned long long key_k = s_prefix;                         // the kk-th smallest key (under mask)
+    const int quota = s_need;                                          // how many of the rows tied with it (under mask) belong to the answer
     // descending row order: everything below key_k, and the first `quota` ties met
     for (int64_t top = n; top > 0; top -= kRsThreads) {
         const int64_t i = top - 1 - tid;
@@ -159,7 +235,7 @@ select_radix_kernel(const double *__restrict__ dist, int64_t n, int64_t dist_ld,
         double d = 0.0;
         if (i >= 0) {
             d = row[i];
-            const unsigned long long key = (unsigned long long)__double_as_longlong(d);
+            const unsigned long long key = (unsigned long long)__double_as_longlong(d) & mask;
             less = key < key_k; tie = key == key_k;
         }
         const unsigned int tie_mask = __ballot_sync(kFull, tie);
@@ -207,7 +283,7 @@ select_radix_kernel(const double *__restrict__ dist, int64_t n, int64_t dist_ld,
 }
 
 static int64_t sparse_query_tile(int64_t n, int64_t nq) {
-    const int64_t budget = (int64_t)256 << 20;   // bytes of distance scratch per tile
+    const int64_t budget = (int64_t)96 << 20;    // bytes of distance scratch per tile: the selection's seven passes hit in L2
     int64_t t = budget / (8 * (n > 0 ? n : 1));
     if (t < 1) t = 1;
     if (t > 16384) t = 16384;
@@ -227,10 +303,11 @@ extern "C" size_t morna_knn_exact_sparse_workspace_bytes(int64_t n, int64_t nq, 
            morna_select_topk_workspace_bytes(n, tile, k) + 256;
 }
 
-extern "C" int morna_knn_exact_sparse(const int64_t *row_off, const int32_t *cols, const float *vals, const double *pp, int64_t n,
-                                      int32_t dim, int32_t id_base, const double *queries, int64_t nq, int64_t q_ld, int32_t k,
-                                      int32_t *out_ids, double *out_dist, void *workspace, size_t workspace_bytes, void *stream) {
-    if (!row_off || !cols || !vals || !pp || !queries || !out_ids || !out_dist || n <= 0 || nq < 0 || dim <= 0 || q_ld < dim || k <= 0)
+extern "C" int morna_knn_exact_sparse(const int64_t *row_off, const int32_t *cols, const float *vals, const int32_t *plan,
+                                      const double *pp, int64_t n, int32_t dim, int32_t id_base, const double *queries, int64_t nq,
+                                      int64_t q_ld, int32_t k, int32_t *out_ids, double *out_dist, void *workspace,
+                                      size_t workspace_bytes, void *stream) {
+    if (!row_off || !cols || !vals || !plan || !pp || !queries || !out_ids || !out_dist || n <= 0 || nq < 0 || dim <= 0 || q_ld < dim || k <= 0)
         return MORNA_ERR_INVALID_ARGUMENT;
     if (!workspace || workspace_bytes < morna_knn_exact_sparse_workspace_bytes(n, nq, k)) return MORNA_ERR_WORKSPACE_TOO_SMALL;
     if (nq == 0) return MORNA_OK;
@@ -247,11 +324,10 @@ extern "C" int morna_knn_exact_sparse(const int64_t *row_off, const int32_t *col
     MORNA_LAUNCH_CHECK();
     for (int64_t q0 = 0; q0 < nq; q0 += tile) {
         const int64_t cnt = nq - q0 < tile ? nq - q0 : tile;
-        for (int64_t y0 = 0; y0 < cnt; y0 += 65535) {         // grid.y limit
-            const int64_t ny = cnt - y0 < 65535 ? cnt - y0 : 65535;
-            dim3 grid((unsigned)((n + kSparseThreads - 1) / kSparseThreads), (unsigned)ny);
-            sparse_distances_kernel<<<grid, kSparseThreads, 0, s>>>(row_off, cols, vals, pp, n, queries + (q0 + y0) * q_ld, q_ld,
-                                                                   qq + q0 + y0, dist + y0 * n, n);
+        {                                                     // cnt <= 16384 queries per tile: grid.y stays small
+            dim3 grid((unsigned)((n + kSparseThreads - 1) / kSparseThreads), (unsigned)((cnt + kSparseQT - 1) / kSparseQT));
+            sparse_distances_kernel<<<grid, kSparseThreads, 0, s>>>(row_off, cols, vals, plan, pp, n, queries + q0 * q_ld, cnt, q_ld,
+                                                                   qq + q0, dist, n);
             MORNA_LAUNCH_CHECK();
         }
         if (k <= kRsMaxK && n <= 0x7fffffff) {

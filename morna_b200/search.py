@@ -81,6 +81,38 @@ class MornaSearch(object):
                                                 _lib.dev_ptr(self.pp), _lib.stream_ptr()), "morna_row_norms")
         self._build_csr()
 
+    def _summation_plans(self, counts, row_off, cols):
+        """int32 per row for morna_knn_exact_sparse (layout in include/morna_b200.h): how a row of <= 3 non-zeros reproduces
+        the dense kernels' summation tree with three accumulators; bit 30 for longer rows (generic emulation)."""
+        n, dev = counts.shape[0], self.device
+        c = torch.full((n, 3), -1, dtype=torch.int64, device=dev)
+        for e in range(3):
+            have = counts > e
+            c[have, e] = cols[(row_off[:-1][have] + e).clamp_max(cols.numel() - 1)].to(torch.int64)
+        lane = (c >> 2) & 31
+        l0, l1, l2 = lane[:, 0], lane[:, 1], lane[:, 2]
+
+        def lowbit(x):
+            return x & (-x)
+        lab, lac, lbc = lowbit(l0 ^ l1), lowbit(l0 ^ l2), lowbit(l1 ^ l2)
+        m = torch.maximum(torch.maximum(lab, lac), lbc)
+        zero, one, two = (torch.full((n,), v, dtype=torch.int64, device=dev) for v in (0, 1, 2))
+        t1 = torch.where(l0 == l1, zero, one)
+        # three entries: equal lanes share an accumulator; of three distinct lanes the pair that meets first in the butterfly
+        # (largest lowest-differing bit) takes accumulators 0 and 1
+        t1_3 = torch.where(l0 == l1, zero, torch.where(l0 == l2, one, torch.where(l1 == l2, one,
+                           torch.where(lab == m, one, torch.where(lac == m, two, zero)))))
+        t2_3 = torch.where((l0 == l1) & (l1 == l2), zero, torch.where(l0 == l1, one, torch.where(l0 == l2, zero,
+                           torch.where(l1 == l2, one, torch.where(lab == m, two, one)))))
+        t0_3 = torch.where((l0 != l1) & (l0 != l2) & (l1 != l2) & (lab != m) & (lac != m), two, zero)
+        three = counts == 3
+        t0 = torch.where(three, t0_3, zero)
+        t1 = torch.where(three, t1_3, torch.where(counts == 2, t1, zero))
+        t2 = torch.where(three, t2_3, zero)
+        plan = t0 | (t1 << 2) | (t2 << 4) | (counts.to(torch.int64) << 8)
+        plan = torch.where(counts > 3, torch.full_like(plan, 1 << 30), plan)
+        return plan.to(torch.int32).contiguous()
+
     def _build_csr(self):
         """A sparse index (every row has at most morna_sparse_max_nnz() non-zero buckets -- an index built from a handful
         of junctions, like the reference's fixture) also keeps its rows in CSR form: exact search then costs nnz(row)
@@ -102,7 +134,7 @@ class MornaSearch(object):
         if cols.numel() == 0:                              # all-zero index: keep valid pointers
             cols = torch.zeros(1, dtype=torch.int32, device=self.device)
             vals = torch.zeros(1, dtype=torch.float32, device=self.device)
-        self.csr = (row_off, cols, vals)
+        self.csr = (row_off, cols, vals, self._summation_plans(counts, row_off, cols))
         # Which path answers a batch.  Rows with the same non-zero buckets can be parallel to each other (one bucket:
         # always), i.e. tie from every query's point of view; when the largest such group is wider than the tensor
         # path's candidate lists, its queries would all overflow into the exact scan -- then the CSR exact path answers
@@ -234,10 +266,11 @@ class MornaSearch(object):
             ids_k = out_ids if k_eff == k else torch.empty((nq, k_eff), dtype=torch.int32, device=dev)
             d_k = out_d if k_eff == k else torch.empty((nq, k_eff), dtype=torch.float64, device=dev)
             if self.csr is not None and bool(torch.isfinite(queries).all()):
-                row_off, cols, vals = self.csr
+                row_off, cols, vals, plan = self.csr
                 ws = self._workspace(self.lib.morna_knn_exact_sparse_workspace_bytes(n, nq, k_eff), "sparse")
                 _lib.check(self.lib.morna_knn_exact_sparse(
-                    _lib.dev_ptr(row_off), _lib.dev_ptr(cols), _lib.dev_ptr(vals), _lib.dev_ptr(self.pp), n, self.dim, self.row_lo,
+                    _lib.dev_ptr(row_off), _lib.dev_ptr(cols), _lib.dev_ptr(vals), _lib.dev_ptr(plan), _lib.dev_ptr(self.pp), n,
+                    self.dim, self.row_lo,
                     _lib.ptr(queries), nq, q_ld, k_eff, _lib.dev_ptr(ids_k), _lib.dev_ptr(d_k), _lib.dev_ptr(ws), ws.numel(),
                     _lib.stream_ptr()), "morna_knn_exact_sparse")
                 if k_eff != k:
