@@ -287,6 +287,15 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = nq * world * args.steps / e2e_s
 
+    # ---- the same batches given as sample ids (`search -q`: the queries are stored rows): 4 bytes per query cross PCIe
+    host_rows = rows.to(torch.int64).cpu().pin_memory()
+    pipeline_ms(torch, srch, [host_rows] * 3, K)
+    barrier()
+    t0 = time.perf_counter()
+    pipeline_ms(torch, srch, [host_rows] * args.steps, K)
+    barrier()
+    e2e_ids_value = nq * world * args.steps / max_over_ranks(time.perf_counter() - t0)
+
     # ---- dominant kernel alone, CUDA events on its stream; the step's own fraction beside it
     roofline = dominant_kernel_roofline(torch, lib, _lib, srch, queries64, peaks)
     step_flops = 2.0 * nq * n_samples * DIM
@@ -357,6 +366,10 @@ def main():
                 "config": workload_config(n_samples, nq, world),
                 "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(host_q.numel() * host_q.element_size()),
                         "d2h_bytes_per_step": int(nq * K * 4 + nq * K * 8)},
+                "e2e_queries_by_sample_id": {"value": e2e_ids_value, "unit": "queries/s", "h2d_bytes_per_step": int(nq * 8),
+                                             "d2h_bytes_per_step": int(nq * K * 4 + nq * K * 8),
+                                             "what": "the same step with the queries named by internal id (stored rows, `search -q`): "
+                                                     "ids in, host ids + distances out; PCIe no longer carries 49 MB of vectors per step"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "single_query": single,
                 "cpu_baseline": cpu, "peaks": peaks["source"]}
         line.update(extras)
@@ -411,13 +424,34 @@ def rows_sharded_line(torch, td, synth, MornaSearch, device, rank, world, n_rows
     def step(queries):
         return mdist.sharded_batched_search(srch, queries, K, check_overflow=False)
 
-    def step_e2e():
-        qd = host_q.to(device, non_blocking=True).to(torch.float64)
-        ids, d = step(qd)
-        if rank == 0:
-            host_ids.copy_(ids, non_blocking=True)
-            host_d.copy_(d, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    copy_stream = torch.cuda.Stream(device=device)
+    stage = [torch.empty((N_QUERIES, DIM), dtype=torch.float32, device=device) for _ in range(2)]
+    staged, consumed = [torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)]
+
+    def run_e2e(count):
+        """`count` steps from pinned host queries to host results: step i+1's host->device copy runs on a copy stream under
+        step i's kernels (two device staging buffers); rank 0 copies every step's ids + distances back."""
+        cur = torch.cuda.current_stream(device)
+
+        def prefetch(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[i & 1])
+                stage[i & 1].copy_(host_q, non_blocking=True)
+                staged[i & 1].record(copy_stream)
+        for ev in consumed:
+            ev.record(cur)
+        prefetch(0)
+        for i in range(count):
+            cur.wait_event(staged[i & 1])
+            qd = stage[i & 1].to(torch.float64)
+            consumed[i & 1].record(cur)
+            if i + 1 < count:
+                prefetch(i + 1)
+            ids, d = step(qd)
+            if rank == 0:
+                host_ids.copy_(ids, non_blocking=True)
+                host_d.copy_(d, non_blocking=True)
+        cur.synchronize()
 
     for _ in range(3):
         ids, d = step(q)
@@ -432,12 +466,10 @@ def rows_sharded_line(torch, td, synth, MornaSearch, device, rank, world, n_rows
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1) / steps)
-    for _ in range(2):
-        step_e2e()
+    run_e2e(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        step_e2e()
+    run_e2e(steps)
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) / steps * 1e3)
     # phases of one step on this rank (CUDA events around the calls of the sharded search)
@@ -504,6 +536,38 @@ def single_query_line(torch, lib, _lib, synth, device, peaks):
     side.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / reps
     assert torch.equal(out_i, ids) and torch.equal(out_d, d)
+    # throughput with two queries in flight: a second stream with its own workspace and outputs; the last CTA's selection
+    # and the launch gap of one query then run under the next query's scan (per-query latency is unchanged)
+    other = torch.cuda.Stream(device=device)
+    with torch.cuda.stream(other):
+        ids2, d2 = srch.single_search_device(q, K)                 # creates this stream's workspace
+        sws2, flag2 = srch._sws, srch._sfallback
+        out_i2 = torch.empty((1, K), dtype=torch.int32, device=device)
+        out_d2 = torch.empty((1, K), dtype=torch.float64, device=device)
+
+        def call2():
+            _lib.check(lib.morna_knn_single(_lib.dev_ptr(srch.vectors), _lib.dev_ptr(srch.pp), n, DIM, srch.ld, 0, _lib.dev_ptr(q), K,
+                                            _lib.dev_ptr(out_i2), _lib.dev_ptr(out_d2), _lib.dev_ptr(flag2),
+                                            _lib.dev_ptr(sws2), sws2.numel(), _lib.stream_ptr()), "morna_knn_single")
+        for _ in range(3):
+            call2()
+        graph2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph2, stream=other):
+            call2()
+    other.synchronize()
+    f0, f1, f2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    torch.cuda.synchronize(device)
+    f0.record(side)
+    other.wait_event(f0)
+    for _ in range(reps // 2):
+        with torch.cuda.stream(side):
+            graph.replay()
+        with torch.cuda.stream(other):
+            graph2.replay()
+    f1.record(side); f2.record(other)
+    torch.cuda.synchronize(device)
+    us2 = max(f0.elapsed_time(f1), f0.elapsed_time(f2)) * 1e3 / (2 * (reps // 2))
+    assert torch.equal(out_i2, ids) and torch.equal(out_d2, d) and torch.equal(out_i, ids)
     # end to end: host query in (pinned), host ids + distances out, one query at a time through the public call
     hq = q.cpu().pin_memory()
     for _ in range(5):
@@ -514,6 +578,7 @@ def single_query_line(torch, lib, _lib, synth, device, peaks):
     e2e_us = (time.perf_counter() - t0) / 50 * 1e6
     assert int(hi_[0, 0]) == n // 3
     gbs = 4.0 * n * DIM / (us * 1e-6) / 1e9
+    gbs2 = 4.0 * n * DIM / (us2 * 1e-6) / 1e9
     traffic = None
     prof = os.path.join(ROOT, "profiles", "r01_step_summary.json")     # dram bytes per launch from the committed ncu capture
     if os.path.exists(prof):
@@ -521,6 +586,9 @@ def single_query_line(torch, lib, _lib, synth, device, peaks):
             traffic = json.load(fh).get("scan64_dram_bytes_21504x3000")
     return {"workload": "21504 samples x 3000 features, one query, exact top-100 (the 258 MB matrix exceeds L2)",
             "us_per_query": us, "queries_per_s": 1e6 / us, "kernel": "scan64_select_kernel (one launch per query)",
+            "two_in_flight": {"us_per_query": us2, "queries_per_s": 1e6 / us2, "achieved": gbs2, "frac": gbs2 / peaks["hbm_gbs"],
+                              "what": "the same call replayed alternately on two streams, each with its own workspace: throughput of a stream of "
+                                      "single queries (one query's selection tail and launch gap hide under the next query's scan)"},
             "e2e": {"us_per_query": e2e_us, "queries_per_s": 1e6 / e2e_us, "h2d_bytes": DIM * 8, "d2h_bytes": K * 12,
                     "what": "MornaSearch.exact_search_batch with one host query: pinned copy in, kernel, ids + distances copied out, synchronous"},
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],

@@ -174,6 +174,10 @@ int morna_select_topk(const double *keys, const int32_t *ids, int64_t n, int64_t
  * over the concatenation (ids are distinct across shards), by rank counting instead of a selection. */
 int morna_merge_sorted_topk(const double *dists, const int32_t *ids, int32_t n_lists, int64_t nq,
                             int32_t k_in, int32_t k_out, int32_t *out_ids, double *out_dist, void *stream);
+/* The same merge straight out of an all-gather of packed per-rank buffers: rank g contributes nq*k_in doubles
+ * (distances) followed by nq*k_in int32 (ids); `packed` [dev] is these n_lists buffers back to back (nq*k_in even). */
+int morna_merge_packed_topk(const void *packed, int32_t n_lists, int64_t nq, int32_t k_in, int32_t k_out,
+                            int32_t *out_ids, double *out_dist, void *stream);
 
 /* exact_search_nn for nq queries in one call (morna.py:681-712): distances + top-k.
  * Internally tiles the queries so the distance scratch stays bounded. */

@@ -56,6 +56,7 @@ _SIGNATURES = {
     "morna_select_topk": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_i32, _c_i64, _c_i32, _c_vp, _c_vp,
                                          _c_vp, _c_sz, _c_vp]),
     "morna_merge_sorted_topk": (ctypes.c_int, [_c_vp, _c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_vp, _c_vp, _c_vp]),
+    "morna_merge_packed_topk": (ctypes.c_int, [_c_vp, _c_i32, _c_i64, _c_i32, _c_i32, _c_vp, _c_vp, _c_vp]),
     "morna_knn_exact_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_i32]),
     "morna_knn_exact": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i32, _c_i64, _c_i32, _c_vp, _c_i64, _c_i64,
                                        _c_i32, _c_vp, _c_vp, _c_vp, _c_sz, _c_vp]),

@@ -1432,6 +1432,7 @@ extern "C" int morna_knn_batched_approx(const void *hs, int64_t ld_h, const floa
 namespace morna {
 // k-th largest of the n_lists * k lower bounds the ranks gathered for a query (one warp per query, bisection on the
 // monotone keys): at least k distinct rows over all shards have a true cosine >= the result.
+template <int kPerLane>
 __global__ void __launch_bounds__(256)
 union_kth_kernel(const float *__restrict__ vals, int32_t n_lists, int64_t nq, int32_t k, float *__restrict__ bound) {
     const int lane = threadIdx.x & 31;
@@ -1439,15 +1440,33 @@ union_kth_kernel(const float *__restrict__ vals, int32_t n_lists, int64_t nq, in
     if (q >= nq) return;
     const int total = n_lists * k;
     uint32_t best = 0;
-    for (int bit = 31; bit >= 0; --bit) {
-        const uint32_t trial = best | (1u << bit);
-        int c = 0;
-        for (int e = lane; e < total; e += 32) {
-            const int g = e / k, j = e - g * k;
-            c += float_key(vals[((int64_t)g * nq + q) * k + j]) >= trial;
+    if (kPerLane > 0) {                       // the values fit in registers: one load each, 32 counting steps on registers
+        uint32_t key[kPerLane > 0 ? kPerLane : 1];
+#pragma unroll
+        for (int j = 0; j < kPerLane; ++j) {
+            const int e = j * 32 + lane;
+            key[j] = 0u;                      // below every real key
+            if (e < total) { const int g = e / k, i = e - g * k; key[j] = float_key(vals[((int64_t)g * nq + q) * k + i]); }
         }
-        c = __reduce_add_sync(kFull, c);
-        if (c >= k) best = trial;
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t trial = best | (1u << bit);
+            int c = 0;
+#pragma unroll
+            for (int j = 0; j < kPerLane; ++j) c += key[j] >= trial;
+            c = __reduce_add_sync(kFull, c);
+            if (c >= k) best = trial;
+        }
+    } else {
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t trial = best | (1u << bit);
+            int c = 0;
+            for (int e = lane; e < total; e += 32) {
+                const int g = e / k, j = e - g * k;
+                c += float_key(vals[((int64_t)g * nq + q) * k + j]) >= trial;
+            }
+            c = __reduce_add_sync(kFull, c);
+            if (c >= k) best = trial;
+        }
     }
     if (lane == 0) bound[q] = best ? key_float(best) : -INFINITY;     // fewer than k values in all: no bound
 }
@@ -1456,7 +1475,11 @@ union_kth_kernel(const float *__restrict__ vals, int32_t n_lists, int64_t nq, in
 extern "C" int morna_union_kth_bound(const float *vals, int32_t n_lists, int64_t nq, int32_t k, float *bound, void *stream) {
     if (!vals || !bound || n_lists <= 0 || nq < 0 || k <= 0) return MORNA_ERR_INVALID_ARGUMENT;
     if (nq == 0) return MORNA_OK;
-    morna::union_kth_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, (cudaStream_t)stream>>>(vals, n_lists, nq, k, bound);
+    const unsigned grid = (unsigned)((nq + 7) / 8);
+    const int64_t total = (int64_t)n_lists * k;
+    if (total <= 32 * 8) morna::union_kth_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(vals, n_lists, nq, k, bound);
+    else if (total <= 32 * 32) morna::union_kth_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(vals, n_lists, nq, k, bound);
+    else morna::union_kth_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(vals, n_lists, nq, k, bound);
     MORNA_LAUNCH_CHECK();
     return MORNA_OK;
 }

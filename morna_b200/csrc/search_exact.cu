@@ -402,7 +402,8 @@ constexpr int kMergeThreads = 128;
 
 __global__ void __launch_bounds__(kMergeThreads)
 merge_sorted_topk_kernel(const double *__restrict__ dists, const int32_t *__restrict__ ids, int32_t n_lists, int64_t nq,
-                         int32_t k_in, int32_t k_out, int32_t *__restrict__ out_ids, double *__restrict__ out_dist) {
+                         int32_t k_in, int32_t k_out, int64_t dist_list_stride, int64_t id_list_stride,
+                         int32_t *__restrict__ out_ids, double *__restrict__ out_dist) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sd = reinterpret_cast<double *>(smem_raw);                 // [n_lists * k_in]
     int32_t *si = reinterpret_cast<int32_t *>(sd + (size_t)n_lists * k_in);
@@ -410,8 +411,8 @@ merge_sorted_topk_kernel(const double *__restrict__ dists, const int32_t *__rest
     const int total = n_lists * k_in;
     for (int e = threadIdx.x; e < total; e += kMergeThreads) {
         const int g = e / k_in, j = e - g * k_in;
-        const int64_t src = ((int64_t)g * nq + q) * k_in + j;
-        sd[e] = dists[src]; si[e] = ids[src];
+        const int64_t src = q * k_in + j;                              // lists may sit anywhere: a stride per list
+        sd[e] = dists[(int64_t)g * dist_list_stride + src]; si[e] = ids[(int64_t)g * id_list_stride + src];
     }
     for (int i = threadIdx.x; i < k_out; i += kMergeThreads) { out_ids[q * k_out + i] = -1; out_dist[q * k_out + i] = INFINITY; }
     __syncthreads();
@@ -447,7 +448,26 @@ extern "C" int morna_merge_sorted_topk(const double *dists, const int32_t *ids, 
     if (smem > 200 * 1024 || nq > 0x7fffffff) return MORNA_ERR_INVALID_ARGUMENT;
     { int rca = ensure_dynamic_smem((const void *)morna::merge_sorted_topk_kernel, smem); if (rca != MORNA_OK) return rca; }
     morna::merge_sorted_topk_kernel<<<(unsigned)nq, morna::kMergeThreads, smem, (cudaStream_t)stream>>>(
-        dists, ids, n_lists, nq, k_in, k_out, out_ids, out_dist);
+        dists, ids, n_lists, nq, k_in, k_out, nq * k_in, nq * k_in, out_ids, out_dist);
+    MORNA_LAUNCH_CHECK();
+    return MORNA_OK;
+}
+
+// The same merge straight out of an all-gather of PACKED per-rank buffers: rank g's buffer is nq*k_in doubles
+// (distances) followed by nq*k_in int32 (ids), and the gathered tensor is these buffers back to back.
+extern "C" int morna_merge_packed_topk(const void *packed, int32_t n_lists, int64_t nq, int32_t k_in, int32_t k_out,
+                                       int32_t *out_ids, double *out_dist, void *stream) {
+    if (!packed || !out_ids || !out_dist || n_lists <= 0 || nq < 0 || k_in <= 0 || k_out <= 0) return MORNA_ERR_INVALID_ARGUMENT;
+    if (nq == 0) return MORNA_OK;
+    const size_t smem = (size_t)n_lists * k_in * (sizeof(double) + sizeof(int32_t));
+    if (smem > 200 * 1024 || nq > 0x7fffffff) return MORNA_ERR_INVALID_ARGUMENT;
+    { int rca = ensure_dynamic_smem((const void *)morna::merge_sorted_topk_kernel, smem); if (rca != MORNA_OK) return rca; }
+    const int64_t per_rank_bytes = nq * k_in * 12;                     // 8-byte aligned: nq*k_in*12 is a multiple of 4; require of 8
+    if (per_rank_bytes % 8) return MORNA_ERR_INVALID_ARGUMENT;
+    const double *dists = (const double *)packed;
+    const int32_t *ids = (const int32_t *)((const unsigned char *)packed + nq * k_in * 8);
+    morna::merge_sorted_topk_kernel<<<(unsigned)nq, morna::kMergeThreads, smem, (cudaStream_t)stream>>>(
+        dists, ids, n_lists, nq, k_in, k_out, per_rank_bytes / 8, per_rank_bytes / 4, out_ids, out_dist);
     MORNA_LAUNCH_CHECK();
     return MORNA_OK;
 }

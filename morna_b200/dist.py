@@ -121,22 +121,35 @@ def sharded_batched_search(search, queries, k, group=None, check_overflow=True):
     every = torch.empty((world,) + tuple(vals.shape), dtype=vals.dtype, device=vals.device)
     td.all_gather_into_tensor(every, vals, group=group)
     bound = search.union_kth_bound(every, k)
-    ids, dists = search.batched_finish_bound(bound, check_overflow=check_overflow)
-    return gather_merge_packed(ids, dists, k, group)
+    nq = queries.shape[0]
+    mine = torch.empty(nq * k * 12, dtype=torch.uint8, device=queries.device)      # the send buffer: the lists are written into it
+    views = (mine[nq * k * 8:].view(torch.int32).view(nq, k), mine[:nq * k * 8].view(torch.float64).view(nq, k))
+    search.batched_finish_bound(bound, check_overflow=check_overflow, out=views)
+    return gather_merge_packed(views[0], views[1], k, group, packed=mine)
 
 
-def gather_merge_packed(ids, dists, k, group=None):
+def gather_merge_packed(ids, dists, k, group=None, packed=None):
     """All-gather of every rank's sorted [nq x k] lists in ONE collective (distances and ids packed into one byte
-    buffer per rank), then the rank-counting merge."""
+    buffer per rank: `packed`, or packed here), then the rank-counting merge."""
     import torch.distributed as td
     world = td.get_world_size(group)
     nq, k_in = ids.shape
     nd, ni = nq * k_in * 8, nq * k_in * 4
-    mine = torch.empty(nd + ni, dtype=torch.uint8, device=ids.device)
-    mine[:nd].view(torch.float64).copy_(dists.reshape(-1))
-    mine[nd:].view(torch.int32).copy_(ids.reshape(-1))
+    mine = packed
+    if mine is None:
+        mine = torch.empty(nd + ni, dtype=torch.uint8, device=ids.device)
+        mine[:nd].view(torch.float64).copy_(dists.reshape(-1))
+        mine[nd:].view(torch.int32).copy_(ids.reshape(-1))
     every = torch.empty((world, nd + ni), dtype=torch.uint8, device=ids.device)
     td.all_gather_into_tensor(every, mine, group=group)
-    gd = every[:, :nd].contiguous().view(torch.float64).view(world, nq, k_in)
-    gi = every[:, nd:].contiguous().view(torch.int32).view(world, nq, k_in)
-    return merge_sorted_lists(gi, gd, k)
+    if (nq * k_in) % 2:                       # odd element count: the packed ids would not be 8-byte aligned per rank
+        gd = every[:, :nd].contiguous().view(torch.float64).view(world, nq, k_in)
+        gi = every[:, nd:].contiguous().view(torch.int32).view(world, nq, k_in)
+        return merge_sorted_lists(gi, gd, k)
+    lib = _lib.load()
+    out_i = torch.empty((nq, k), dtype=torch.int32, device=ids.device)
+    out_d = torch.empty((nq, k), dtype=torch.float64, device=ids.device)
+    with torch.cuda.device(ids.device):
+        _lib.check(lib.morna_merge_packed_topk(_lib.dev_ptr(every), world, nq, k_in, k, _lib.dev_ptr(out_i), _lib.dev_ptr(out_d),
+                                               _lib.stream_ptr()), "morna_merge_packed_topk")
+    return out_i, out_d

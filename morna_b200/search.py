@@ -438,19 +438,24 @@ class MornaSearch(object):
                        "morna_union_kth_bound")
         return out
 
-    def batched_finish_bound(self, bound, check_overflow=True):
+    def batched_finish_bound(self, bound, check_overflow=True, out=None):
         """Second half: `bound` float32 [nq] = union_kth_bound of every rank's batched_score_bound result.  Returns this
         rank's (ids, dists), sorted under the reference order with GLOBAL ids; together the ranks' lists hold the global
         top-k (each rank re-ranks only its rows whose score can still reach the global k-th place)."""
         queries, k, tensor, st = self._bound_state
         self._bound_state = None
         if not tensor:
-            return self.exact_search_device(queries, k, allow_single=False)
+            ids, d = self.exact_search_device(queries, k, allow_single=False)
+            if out is not None:
+                out[0].copy_(ids); out[1].copy_(d)
+                return out
+            return ids, d
         overflow, stats, ws = st
         nq, dev = queries.shape[0], self.device
         n = self.row_hi - self.row_lo
-        out_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
-        out_d = torch.empty((nq, k), dtype=torch.float64, device=dev)
+        # `out`: caller-provided (ids int32 [nq x k], dists float64 [nq x k]) -- e.g. views of a packed send buffer
+        out_ids = out[0] if out is not None else torch.empty((nq, k), dtype=torch.int32, device=dev)
+        out_d = out[1] if out is not None else torch.empty((nq, k), dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
             _lib.check(self.lib.morna_knn_batched_finalize(n, nq, self.dim, k, _lib.dev_ptr(bound), _lib.dev_ptr(overflow),
                                                            _lib.dev_ptr(stats), _lib.dev_ptr(ws), ws.numel(), _lib.stream_ptr()),
@@ -465,8 +470,9 @@ class MornaSearch(object):
         return out_ids, out_d
 
     def search_batches(self, batches, k, depth=2, side_job=False):
-        """Streams query batches through the GPU: generator over ``batches`` (each a numpy
-        [nq x dim] float32/float64 array) yielding ``(ids, dists)`` numpy arrays in order -- the same
+        """Streams query batches through the GPU: generator over ``batches`` (each a numpy or torch
+        [nq x dim] float32/float64 array, or a 1-D integer array of INTERNAL IDS whose stored rows are the queries, as
+        ``search -q``) yielding ``(ids, dists)`` numpy arrays in order -- the same
         results as ``exact_search_batch`` per batch.  ``depth`` batches are in flight, each on its own
         CUDA stream with its own pinned staging buffers and workspace, so batch i+1's host->device
         copy and batch i-1's device->host copy overlap batch i's kernels."""
@@ -485,6 +491,41 @@ class MornaSearch(object):
             yield pipe.collect()
             pending -= 1
 
+    def _single_query_host(self, query, k):
+        """One host query through the single-query kernel with persistent pinned staging: one host->device copy (the
+        query), one launch, one device->host copy (distances, ids and the fallback flag packed in one buffer), one stream
+        synchronisation.  Returns numpy (ids [1 x k], dists [1 x k]) or None when the generic path must answer."""
+        n, dev = self.row_hi - self.row_lo, self.device
+        if n == 0 or k <= 0 or min(k, n) > 512 or self.csr is not None:
+            return None
+        state = self.__dict__.setdefault("_single_host", {})
+        st = state.get(k)
+        with torch.cuda.device(dev):
+            if st is None:
+                nbytes = 8 * k + 4 * k + 8
+                st = state[k] = {"h_q": torch.empty(self.dim, dtype=torch.float64).pin_memory(),
+                                 "d_q": torch.empty(self.dim, dtype=torch.float64, device=dev),
+                                 "d_out": torch.zeros(nbytes, dtype=torch.uint8, device=dev),
+                                 "h_out": torch.empty(nbytes, dtype=torch.uint8).pin_memory()}
+            st["h_q"].numpy()[:] = query
+            st["d_q"].copy_(st["h_q"], non_blocking=True)
+            d_out = st["d_out"]
+            dist_v, ids_v, flag_v = d_out[:8 * k].view(torch.float64), d_out[8 * k:12 * k].view(torch.int32), d_out[12 * k:12 * k + 4].view(torch.int32)
+            k_eff = min(k, n)
+            if k_eff < k:
+                ids_v.fill_(-1); dist_v.fill_(float("inf"))
+            sws = self._workspace(self.lib.morna_knn_single_workspace_bytes(n), "single")
+            _lib.check(self.lib.morna_knn_single(
+                _lib.dev_ptr(self.vectors), _lib.dev_ptr(self.pp), n, self.dim, self.ld, self.row_lo, _lib.dev_ptr(st["d_q"]), k_eff,
+                _lib.dev_ptr(ids_v), _lib.dev_ptr(dist_v), _lib.dev_ptr(flag_v), _lib.dev_ptr(sws), sws.numel(), _lib.stream_ptr()),
+                "morna_knn_single")
+            st["h_out"].copy_(d_out, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+        out = st["h_out"].numpy()
+        if int(out[12 * k:12 * k + 4].view(np.int32)[0]):
+            return None
+        return out[8 * k:12 * k].view(np.int32).reshape(1, k).copy(), out[:8 * k].view(np.float64).reshape(1, k).copy()
+
     def exact_search_batch(self, queries, k, tensor_cores=None):
         """Host entry: queries numpy [nq x dim] (float32 or float64) -> numpy (ids, dists).
         float32 queries cross PCIe as float32 and are widened (exactly) on the device.  Batches of 64+
@@ -492,6 +533,10 @@ class MornaSearch(object):
         queries = np.ascontiguousarray(queries)
         if queries.dtype != np.float32:
             queries = queries.astype(np.float64, copy=False)
+        if queries.shape[0] == 1 and not tensor_cores:
+            got = self._single_query_host(queries[0], k)
+            if got is not None:
+                return got
         q = torch.from_numpy(queries)
         if q.numel():
             q = q.pin_memory()
@@ -672,6 +717,17 @@ class BatchPipeline(object):
         assert self.head - self.tail < self.depth, "collect() before submitting more than `depth` batches"
         self.head += 1
         q = torch.from_numpy(np.ascontiguousarray(queries)) if isinstance(queries, np.ndarray) else queries
+        by_id = q.dim() == 1 and q.dtype in (torch.int32, torch.int64)      # stored rows as queries (search -q): only ids cross PCIe
+        if by_id:
+            self._size(sl, q.shape[0], torch.float64, staging=False)
+            with torch.cuda.stream(sl.stream):
+                if q.is_cuda:
+                    sl.stream.wait_stream(torch.cuda.current_stream(s.device))
+                rows = q.to(s.device, non_blocking=True).long() - s.row_lo
+                sl.qd = s.vectors[rows, :s.dim].to(torch.float64).contiguous()
+                sl.h2d.record(sl.stream)
+            self._launch(sl)
+            return
         if q.dtype != torch.float32:
             q = q.to(torch.float64)
         resident = q.is_cuda                 # queries already in HBM: no host->device copy
@@ -687,6 +743,11 @@ class BatchPipeline(object):
         with torch.cuda.stream(sl.stream):
             sl.qd = src.to(s.device, non_blocking=True).to(torch.float64).contiguous()   # float32 widens exactly
             sl.h2d.record(sl.stream)
+        self._launch(sl)
+
+    def _launch(self, sl):
+        """Kernels of the slot's batch (queries in sl.qd once sl.h2d fires) on its compute stream."""
+        s, k = self.search, self.k
         n = s.row_hi - s.row_lo
         sl.compute.wait_event(sl.h2d)
         with torch.cuda.stream(sl.compute):

@@ -232,6 +232,9 @@ def test_streaming_batches_equal_the_synchronous_call():
         batches.append(Q if b % 2 == 0 else Q.astype(np.float64))
     batches.append(torch.from_numpy(batches[0]).pin_memory())        # caller-pinned source, no staging copy
     want = [srch.exact_search_batch(np.asarray(B), k, tensor_cores=False) for B in batches]
+    member_ids = np.array([9, 10, 5999, 0, 77] * 20, dtype=np.int64)   # stored rows named by internal id (search -q)
+    batches.append(member_ids)
+    want.append(srch.exact_search_batch(S[member_ids], k, tensor_cores=False))
     for depth in (1, 2, 3):
         got = [(i.copy(), d_.copy()) for i, d_ in srch.search_batches(iter(batches), k, depth=depth)]
         assert len(got) == len(want)
