@@ -64,7 +64,7 @@ class ClockSampler(threading.Thread):
             while not self._stop_evt.is_set():
                 self.rows.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
                                   nv.nvmlDeviceGetCurrentClocksEventReasons(h), nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
-                time.sleep(0.002)
+                time.sleep(0.005)
         except Exception as exc:      # NVML absent: report that instead of clocks
             self.error = "nvml_unavailable:%s" % type(exc).__name__
 
