@@ -21,8 +21,8 @@ constexpr int kS1Cand = 1024;          // candidates ordered by their double dis
 constexpr int kBins = 8192;            // distance histogram: bin = floor(d * kBins / 2), d in [0, 2]
 constexpr int kBinCap = 64;            // rows remembered per bin
 
-struct SingleWs {          // device-side control block at the start of the workspace; ticket and row counter are zero between calls
-    unsigned int scan_ticket, next_row, pad[2];
+struct SingleWs {          // device-side control block at the start of the workspace; the ticket is zero between calls
+    unsigned int scan_ticket, pad[3];
     unsigned long long stamp[8];   // %globaltimer (ns): CTA 0 start, last CTA at the ticket, after the k-th key, at the end;
                                    // 4..7: inside the selection (pivot, filter, k-th of survivors, emission)
 };
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kS1Threads, 2)
 scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict__ pp, int64_t n, int64_t ld,
                      int32_t dim, int32_t id_base, const double *__restrict__ query, int32_t k, int64_t rows_per_warp,
                      double *__restrict__ dist, float *__restrict__ sel, unsigned int *__restrict__ hist,
-                     int32_t *__restrict__ lists, double *__restrict__ ldist, SingleWs *ctl,
+                     int32_t *__restrict__ lists, SingleWs *ctl,
                      int32_t *__restrict__ out_ids, double *__restrict__ out_dist, int32_t *__restrict__ fallback_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *qs = reinterpret_cast<double *>(smem_raw);                 // [ld] query * 2^896
@@ -222,20 +222,9 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
     }
     qq = warp_sum(qq);
 
-    // rows_per_warp > 0 (default): every warp owns a contiguous share of the rows.  rows_per_warp <= 0 (tuning sweep only):
-    // rows are dealt out R at a time from a global counter, the next ticket drawn before the current rows are loaded --
-    // balanced for any N, but measured slower on B200 (21,504 rows: 72 vs 59 us; the contiguous shares stream better).
-    const bool dynamic = rows_per_warp <= 0;
-    auto draw = [&]() -> int64_t {
-        unsigned int b = 0;
-        if (lane == 0) b = atomicAdd(&ctl->next_row, (unsigned int)R);
-        return (int64_t)__shfl_sync(kFull, b, 0);
-    };
     const int64_t gw = (int64_t)blockIdx.x * kS1Warps + warp;
-    int64_t row_begin = dynamic ? draw() : gw * rows_per_warp;
-    int64_t row_end = dynamic ? min(n, row_begin + R) : min(n, row_begin + rows_per_warp);
-  while (row_begin < n) {
-    const int64_t next_begin = dynamic ? draw() : n;
+    const int64_t row_begin = gw * rows_per_warp;
+    const int64_t row_end = min(n, row_begin + rows_per_warp);
     int64_t r = row_begin;
     for (; r + R <= row_end; r += R) {                                 // R whole rows, regular stride
         const float4 *src = reinterpret_cast<const float4 *>(vectors + r * ld);
@@ -287,7 +276,7 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
             sel[r + lane] = -__double2float_rd(d);                     // larger = nearer; monotone in d
             const int bin = min(kBins - 1, (int)(d * (kBins / 2)));
             const unsigned int slot = atomicAdd(hist + bin, 1u);
-            if (slot < kBinCap) { lists[bin * kBinCap + slot] = (int)(r + lane); ldist[bin * kBinCap + slot] = d; }
+            if (slot < kBinCap) lists[bin * kBinCap + slot] = (int)(r + lane);
         }
     }
     for (; r < row_end; ++r) {                                         // leftover rows of this warp, one at a time
@@ -307,12 +296,9 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
             sel[r] = -__double2float_rd(d);
             const int bin = min(kBins - 1, (int)(d * (kBins / 2)));
             const unsigned int slot = atomicAdd(hist + bin, 1u);
-            if (slot < kBinCap) { lists[bin * kBinCap + slot] = (int)r; ldist[bin * kBinCap + slot] = d; }
+            if (slot < kBinCap) lists[bin * kBinCap + slot] = (int)r;
         }
     }
-    row_begin = next_begin;
-    row_end = min(n, row_begin + R);
-  }
     // last CTA to arrive answers the query from all keys
     __threadfence();
     __syncthreads();
@@ -323,7 +309,7 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (tid == 0) { ctl->scan_ticket = 0; ctl->next_row = 0; ctl->stamp[1] = global_ns(); }   // left zeroed for the next call
+    if (tid == 0) { ctl->scan_ticket = 0; ctl->stamp[1] = global_ns(); }   // ticket left zeroed for the next call
     // The distance histogram all CTAs filled (and each bin's first rows) gives the candidates directly:
     // the bin holding the k-th nearest row, and every row in a bin at or below it.
     const int kk = (int)min((int64_t)k, n);
@@ -371,10 +357,7 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
                 if (c == 0) continue;
                 if (c > kBinCap) { s_small[3] = 1; continue; }         // a bin overflowed its row list
                 const int o = atomicAdd(&s_small[2], c);
-                for (int t = 0; t < c; ++t) {                              // row and distance in one round trip
-                    s_cand[o + t] = __ldcg(lists + b * kBinCap + t);
-                    sd[o + t] = __ldcg(ldist + b * kBinCap + t);
-                }
+                for (int t = 0; t < c; ++t) s_cand[o + t] = __ldcg(lists + b * kBinCap + t);
             }
             __syncthreads();
             if (!s_small[3]) count = m;
@@ -382,7 +365,6 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
         __syncthreads();
     }
     if (tid == 0) ctl->stamp[2] = global_ns();
-    const bool have_d = count >= 0;    // the histogram path already put every candidate's distance into sd[]
     if (count < 0) {                   // crowded bins (heavy ties): select from the float keys instead
         select_candidates(sel, n, k, s_cand, s_key, s_idx, s_small, ctl->stamp);
         if (s_small[4]) {
@@ -397,7 +379,7 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
         // writes it straight to its place
         double my_d = INFINITY;
         int my_id = -1;
-        if (tid < count) { const int row = s_cand[tid]; my_d = have_d ? sd[tid] : __ldcg(dist + row); my_id = id_base + row; }
+        if (tid < count) { const int row = s_cand[tid]; my_d = __ldcg(dist + row); my_id = id_base + row; }
         if (tid < 256) { sd[tid] = my_d; si[tid] = my_id; }
         __syncthreads();
         if (tid < count) {
@@ -411,7 +393,7 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
         while (P < count) P <<= 1;
         for (int i = tid; i < P; i += kS1Threads) {
             const int row = i < count ? s_cand[i] : 0;
-            sd[i] = i < count ? (have_d ? sd[i] : __ldcg(dist + row)) : INFINITY;
+            sd[i] = i < count ? __ldcg(dist + row) : INFINITY;
             si[i] = i < count ? id_base + row : -1;
         }
         for (int size = 2; size <= P; size <<= 1) {
@@ -438,13 +420,12 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
     if (tid == 0) ctl->stamp[3] = global_ns();
 }
 
-static int g_single_rows = 0;     // morna_debug_set_tuning key 3: rows per warp pass (0 = automatic); negative: rows dealt out |v| at a
-static int g_single_static = 1;   // time from a global counter instead of the static contiguous split (measured slower: 72 vs 59 us)
-void set_single_tma(int v) { g_single_static = v >= 0; g_single_rows = v < 0 ? -v : v; }
+static int g_single_rows = 0;     // morna_debug_set_tuning key 3: rows per warp pass (0 = automatic)
+void set_single_tma(int v) { g_single_rows = v; }
 
 static int sm_count_s() { return sm_count_current(); }
 
-struct SingleLayout { size_t ctl, hist, lists, ldist, dist, sel, total; };
+struct SingleLayout { size_t ctl, hist, lists, dist, sel, total; };
 static SingleLayout single_layout(int64_t n) {
     SingleLayout w{};
     size_t off = 0;
@@ -452,7 +433,6 @@ static SingleLayout single_layout(int64_t n) {
     w.ctl = take(sizeof(SingleWs));
     w.hist = take((size_t)kBins * sizeof(unsigned int));              // ctl + hist: zero between calls
     w.lists = take((size_t)kBins * kBinCap * sizeof(int32_t));
-    w.ldist = take((size_t)kBins * kBinCap * sizeof(double));
     w.dist = take((size_t)n * sizeof(double));
     w.sel = take((size_t)n * sizeof(float));
     w.total = off + 256;
@@ -462,10 +442,10 @@ static SingleLayout single_layout(int64_t n) {
 template <int R, int U>
 static int launch_scan64(unsigned grid, size_t smem, cudaStream_t s, const float *vectors, const double *pp, int64_t n,
                          int64_t ld, int32_t dim, int32_t id_base, const double *query, int32_t k, int64_t rows_per_warp,
-                         double *dist, float *sel, unsigned int *hist, int32_t *lists, double *ldist, SingleWs *ctl, int32_t *out_ids, double *out_dist, int32_t *fallback) {
+                         double *dist, float *sel, unsigned int *hist, int32_t *lists, SingleWs *ctl, int32_t *out_ids, double *out_dist, int32_t *fallback) {
     { int rca = ensure_dynamic_smem((const void *)scan64_select_kernel<R, U>, smem); if (rca != MORNA_OK) return rca; }
     scan64_select_kernel<R, U><<<grid, kS1Threads, smem, s>>>(vectors, pp, n, ld, dim, id_base, query, k, rows_per_warp,
-                                                              dist, sel, hist, lists, ldist, ctl, out_ids, out_dist, fallback);
+                                                              dist, sel, hist, lists, ctl, out_ids, out_dist, fallback);
     MORNA_LAUNCH_CHECK();
     return MORNA_OK;
 }
@@ -499,7 +479,6 @@ extern "C" int morna_knn_single(const float *vectors, const double *pp, int64_t 
     float *sel = (float *)(ws + w.sel);
     unsigned int *hist = (unsigned int *)(ws + w.hist);
     int32_t *lists = (int32_t *)(ws + w.lists);
-    double *ldist = (double *)(ws + w.ldist);
     size_t smem = (size_t)ld * sizeof(double);
     const size_t tail_bytes = (size_t)kBins * 4 + (size_t)kS1Cand * (4 + 8 + 4);
     static_assert(kBins * 4 >= kS1List * 8, "the survivor lists overlay the histogram copy");
@@ -520,16 +499,11 @@ extern "C" int morna_knn_single(const float *vectors, const double *pp, int64_t 
     int R = rpw < 3 ? (int)rpw : 3;
     if (g_single_rows > 0 && g_single_rows <= 5) R = g_single_rows;
     rpw = (rpw + R - 1) / R * R;
-    int64_t warps = (n + rpw - 1) / rpw;
-    if (!g_single_static) {            // rows dealt out R at a time from a counter: every resident warp takes part
-        warps = (n + R - 1) / R;
-        if (warps > max_warps) warps = max_warps;
-        rpw = 0;
-    }
+    const int64_t warps = (n + rpw - 1) / rpw;
     const unsigned grid = (unsigned)((warps + kS1Warps - 1) / kS1Warps);
 #define MORNA_SCAN64(RR, UU)                                                                                          \
     case RR: return launch_scan64<RR, UU>(grid, smem, s, vectors, pp, n, ld, dim, id_base, query, k, rpw, dist, sel, \
-                                          hist, lists, ldist, ctl, out_ids, out_dist, fallback)
+                                          hist, lists, ctl, out_ids, out_dist, fallback)
     switch (R) {
         MORNA_SCAN64(1, 8); MORNA_SCAN64(2, 4); MORNA_SCAN64(3, 2); MORNA_SCAN64(4, 2); MORNA_SCAN64(5, 1);
     }

@@ -133,6 +133,9 @@ class MornaIndex(object):
         """Runs the device pipeline.  ``n_trees`` is accepted for signature parity and
         ignored (no Annoy forest).  ``id_range=(lo, hi)`` keeps only that slice of
         internal ids on this GPU (multi-GPU index build); ids and the map are global."""
+        if stream is not None and stream != torch.cuda.current_stream(self.device):
+            with torch.cuda.stream(stream):              # copies, allocations, kernels and host reads all on `stream`
+                return self.build(n_trees, verbose, id_range)
         lib, dev = self.lib, self.device
         packed, key_off, row_off, sample, cov = self._rows.finish()
         n_rows, nnz = len(self._rows), int(row_off[-1])
@@ -149,7 +152,7 @@ class MornaIndex(object):
                                       int(self.sample_count), idf.ctypes.data), "morna_idf_host")
 
         with torch.cuda.device(dev):
-            sp = _lib.stream_ptr(stream)
+            sp = _lib.stream_ptr()
             to_dev = lambda a: _pinned(a).to(dev, non_blocking=True)
             d_keys, d_key_off = to_dev(packed), to_dev(key_off)
             d_row_off, d_sample, d_cov = to_dev(row_off), to_dev(sample), to_dev(cov)
