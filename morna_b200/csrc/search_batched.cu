@@ -75,14 +75,22 @@ prep_queries_kernel(const double *__restrict__ queries, int64_t nq, int64_t nq_p
             continue;
         }
         const double *q = queries + row * q_ld;
+        const bool vec_ok = ((q_ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(queries) & 15) == 0);
         double acc = 0.0;
         bool huge = false;                               // the re-rank stages q * 2^896 (f32_scaled_f64)
         for (int c = lane; 4 * c < dim; c += 32) {       // same lane/chunk partition as the scan
+            double a[4];
+            if (vec_ok && 4 * c + 3 < dim) {
+                const double2 lo = *reinterpret_cast<const double2 *>(q + 4 * c), hi = *reinterpret_cast<const double2 *>(q + 4 * c + 2);
+                a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
+            } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) a[t] = (4 * c + t < dim) ? q[4 * c + t] : 0.0;
+            }
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                double a = (4 * c + t < dim) ? q[4 * c + t] : 0.0;
-                huge |= !(fabs(a) < kScaledQueryMax);
-                acc = fma(a, a, acc);
+                huge |= !(fabs(a[t]) < kScaledQueryMax);
+                acc = fma(a[t], a[t], acc);
             }
         }
         acc = warp_sum(acc);
@@ -95,9 +103,17 @@ prep_queries_kernel(const double *__restrict__ queries, int64_t nq, int64_t nq_p
         double res = 0.0;
         for (int c = lane; c < chunks_h; c += 32) {
             __half h[4];
+            double a[4];
+            if (vec_ok && 4 * c + 3 < dim) {
+                const double2 lo = *reinterpret_cast<const double2 *>(q + 4 * c), hi = *reinterpret_cast<const double2 *>(q + 4 * c + 2);
+                a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
+            } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) a[t] = (4 * c + t < dim) ? q[4 * c + t] : 0.0;
+            }
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                double x = (4 * c + t < dim) ? q[4 * c + t] * inv : 0.0;
+                double x = a[t] * inv;
                 h[t] = __float2half_rn((float)x);
                 double r = x - (double)__half2float(h[t]);
                 res = fma(r, r, res);
@@ -939,16 +955,17 @@ kth_warp_kernel(KthParams p, int nq) {
         // stream: lane owns float4 groups lane, lane+32, ...; survivors go to its private list
         const int groups = (count + 3) >> 2;
         bool overflowed = false;
-        for (int g0 = lane; g0 < groups; g0 += 32 * 4) {                     // four 16-byte loads in flight per lane
-            float4 v[4];
+        constexpr int kInFlight = 8;                                         // 16-byte loads in flight per lane (the stream is latency bound)
+        for (int g0 = lane; g0 < groups; g0 += 32 * kInFlight) {
+            float4 v[kInFlight];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kInFlight; ++u) {
                 const int g = g0 + 32 * u;
-                v[u] = g < groups ? *reinterpret_cast<const float4 *>(src + 4 * g)   // rows are 16-byte aligned and padded
+                v[u] = g < groups ? __ldcs(reinterpret_cast<const float4 *>(src + 4 * g))   // rows are 16-byte aligned and padded; read once
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kInFlight; ++u) {
                 const int g = g0 + 32 * u;
                 const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
