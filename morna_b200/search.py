@@ -706,10 +706,16 @@ class BatchPipeline(object):
             seen = getattr(sl, "seen_key", None)
             sl.graph_key = None
             if self.use_graphs and seen == key and sl.ws is not None:
+                # capture_begin / capture_end directly: the torch.cuda.graph context would synchronise the device, run the
+                # garbage collector and empty the allocator cache first -- a stall of several batch times.  Nothing is
+                # allocated between the two calls (every buffer of the step already exists).
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=torch.cuda.current_stream(self.search.device), capture_error_mode="thread_local"):
+                graph.capture_begin(capture_error_mode="thread_local")
+                try:
                     self._score(sl, None)
                     self._rerank_kernels(sl, resume=False)
+                finally:
+                    graph.capture_end()
                 sl.graph, sl.graph_key = graph, key
                 graph.replay()
             else:
