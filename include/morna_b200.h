@@ -323,6 +323,9 @@ int morna_debug_tensor_scores(const void *hs, int64_t ld_h, const float *rho_max
  *   15 re-rank (warp kernel): CTAs per SM (0 = what fits)                   16 re-rank: items per query when not split into phases (0 = 4)
  *   17 side jobs: 0 = helper warps off (resume calls then re-rank everything) */
 int morna_debug_set_tuning(int32_t key, int32_t value);
+/* Experiment hook: [dev] int64[grid * 4] that the pair GEMM's MMA-issuing thread fills with the cycles it spent waiting for
+ * operand tiles (TMA) and for a free accumulator (epilogue), and its total; NULL switches it off (default). */
+int morna_debug_gemm_counters(void *buffer);
 
 #ifdef __cplusplus
 }

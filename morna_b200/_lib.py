@@ -84,6 +84,7 @@ _SIGNATURES = {
     "morna_debug_tensor_scores": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_i64, _c_i32, _c_vp, _c_i64, _c_i64, _c_vp,
                                                  _c_i64, _c_vp, _c_vp, _c_sz, _c_vp]),
     "morna_debug_set_tuning": (ctypes.c_int, [_c_i32, _c_i32]),
+    "morna_debug_gemm_counters": (ctypes.c_int, [_c_vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

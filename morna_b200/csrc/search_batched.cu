@@ -525,6 +525,8 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 }  // namespace gemm
 
 struct GemmParams {
+    int32_t relaxed_ns;    // > 0: epilogue warps sleep this long between polls of the accumulator barrier (key 22)
+    long long *debug;      // optional [gridDim.x][4] cycle counters of the MMA thread (full-barrier wait, accumulator wait, total) and the epilogue
     int32_t nq, n_begin, n_end, kblocks, m_blocks, n_tiles, mode, cap, id_base;
     float *pilot; int64_t pilot_ld;
     const float *thr; float *cand_score; int32_t *cand_id; int32_t *cand_cnt;
@@ -753,7 +755,8 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 const int row_q = m_pair * 2 * BM + (int)rank * BM;
                 const int row_s = p.n_begin + n_tile * BN + (int)rank * BN_HALF;
                 for (int kb = 0; kb < p.kblocks; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    if (p.relaxed_ns > 1) mbar_wait_relaxed(empty_bar(stage), phase ^ 1, 20u);
+                    else mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t a_dst = base + stage * STAGE_BYTES, b_dst = a_dst + A_BYTES;
                     const uint32_t bar0 = mapa_rank0(full_bar(stage));
                     if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
@@ -767,12 +770,18 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (lane == 0 && leader) {     // ===== MMA issuer: one thread of the leader CTA
             constexpr uint32_t idesc = instr_desc_f16(2 * BM, BN, /*fp16*/ 0);
             int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            long long w_full = 0, w_acc = 0;
+            const long long t_begin = clock64();
             for (int t = pair; t < total_tiles; t += pairs) {
+                long long c0 = p.debug ? clock64() : 0;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                if (p.debug) w_acc += clock64() - c0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < p.kblocks; ++kb) {
+                    c0 = p.debug ? clock64() : 0;
                     mbar_wait(full_bar(stage), phase);
+                    if (p.debug) w_full += clock64() - c0;
                     tc_fence_after();
                     const uint32_t a_src = base + stage * STAGE_BYTES, b_src = a_src + A_BYTES;
                     const uint64_t da = smem_desc_sw128(a_src), db = smem_desc_sw128(b_src);
@@ -785,6 +794,7 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 }
                 if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
+            if (p.debug) { p.debug[blockIdx.x * 4 + 0] = w_full; p.debug[blockIdx.x * 4 + 1] = w_acc; p.debug[blockIdx.x * 4 + 2] = clock64() - t_begin; }
         }
     } else if (warp >= THREADS / 32) {     // ===== helper warps: re-rank items of the previous batch
         if (rr.queue) rerank_warp_loop<8, 2>(rr, helper_lists + (warp - THREADS / 32) * 1024, lane, helper_stop);
@@ -798,7 +808,8 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const int col_tile = p.n_begin + n_tile * BN;
             float thr = INFINITY;
             if (p.mode == 1 && row_ok) thr = p.thr[row];
-            mbar_wait(tfull_bar(acc), acc_phase);
+            if (p.relaxed_ns) mbar_wait_relaxed(tfull_bar(acc), acc_phase, (unsigned)p.relaxed_ns);
+            else mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
@@ -1132,6 +1143,8 @@ static int g_rerank_subs = 0;      // key 16: items per query of the unsplit war
 static int g_side_job = 0;         // key 17: 1 = side jobs on: helper warps in the GEMM kernel re-rank the previous batch (measured slower:
                                    // the GEMM's TMA stream and the helpers' gathers queue behind each other)
 static int g_rerank_pipe = 1;      // key 18: CTA-per-query re-rank with software-pipelined row loads
+static long long *g_gemm_debug = nullptr;   // morna_debug_gemm_counters: device buffer for the MMA thread's wait counters
+static int g_gemm_relaxed_ns = 0;  // key 22
 static int g_carveout_hint = 0;    // key 19: ask for the maximum shared-memory carve-out on the batched path's kernels (co-residency across streams)
 static int g_rerank_oneshot = 1;   // key 20: CTA-per-query re-rank launched as one CTA per item (default; 0 = persistent grid): its CTAs retire one by
                                    // one, so the next batch's first kernels start under its tail (1.875 -> 1.834 ms per headline batch)
@@ -1293,6 +1306,7 @@ static int score_impl(const void *hs, int64_t ld_h, const float *rho_max, int64_
     rc = make_tmap(&tmap_s, hs, (uint64_t)n, (uint64_t)ld_h, g_gemm_pair ? gemm2::BN_HALF : gemm::BN);
     if (rc != MORNA_OK) return rc;
     GemmParams gp{};
+    gp.debug = g_gemm_debug; gp.relaxed_ns = g_gemm_relaxed_ns;
     gp.nq = (int32_t)nq; gp.kblocks = (int32_t)(ld_h / gemm::BK); gp.m_blocks = (int32_t)(w.nq_pad / gemm::BM);
     gp.cap = kCandCap; gp.id_base = id_base; gp.pilot = pilot; gp.pilot_ld = w.pilot_ld; gp.thr = thr;
     gp.cand_score = cand_score; gp.cand_id = cand_id; gp.cand_cnt = cand_cnt;
@@ -1673,6 +1687,9 @@ extern "C" int morna_debug_tensor_scores(const void *hs, int64_t ld_h, const flo
  * key 1 = shared-memory pipeline stages of the pair variant (4 or 6). */
 namespace morna { void set_single_tma(int v); void set_acc_pipelined(int v); void set_acc_split(int v); void set_acc_variant(int v); void set_acc_shift(int v); }
 
+/* Experiment hook: device buffer of gridDim.x * 4 int64 that the pair GEMM's MMA thread fills with its wait cycles (NULL = off). */
+extern "C" int morna_debug_gemm_counters(void *buffer) { g_gemm_debug = (long long *)buffer; return MORNA_OK; }
+
 extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
     if (key == 0) g_gemm_pair = value ? 1 : 0;
     else if (key == 3) morna::set_single_tma(value);
@@ -1694,6 +1711,7 @@ extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
     else if (key == 18) g_rerank_pipe = value;
     else if (key == 19) g_carveout_hint = value;
     else if (key == 20) g_rerank_oneshot = value;
+    else if (key == 22) g_gemm_relaxed_ns = value;
 
     else return MORNA_ERR_INVALID_ARGUMENT;
     return MORNA_OK;

@@ -64,6 +64,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// The same wait for warps with slack (epilogue warps waiting for a finished accumulator, the producer waiting for a free
+// stage): sleep between polls instead of spinning -- 128 spinning threads per SM cost issue slots and power the MMAs need.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(ns);
+        if (clock64() - t0 > 4000000000LL) __trap();     // ~2 s
+    }
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
