@@ -443,3 +443,26 @@ def test_approximate_mode_recall_and_distances():
     srch.query_sample = q[0].cpu().tolist()
     ids, dists = srch.search_nn(k)
     assert ids == a_ids[0].tolist() and len(dists) == k
+
+
+def test_streaming_batches_with_k_above_the_tensor_path_limit():
+    """k = 600 > 512 sends every pipeline slot through the FP64 scan on the slot's own stream; each stream has its own
+    scan workspace (two batches in flight used to share one), so depth 2 and 3 return the synchronous call's lists."""
+    rng = np.random.default_rng(600)
+    n, d, k = 5000, 96, 600
+    S = rng.standard_normal((n, d)).astype(np.float32)
+    srch = make_search(S)
+    batches = [S[rng.permutation(n)[:nq]] + np.float32(0.02) * rng.standard_normal((nq, d)).astype(np.float32)
+               for nq in (130, 130, 77, 130, 130, 9)]
+    want = [srch.exact_search_batch(B, k, tensor_cores=False) for B in batches]
+    for depth in (2, 3):
+        got = [(i.copy(), d_.copy()) for i, d_ in srch.search_batches(iter(batches), k, depth=depth)]
+        for (gi, gd), (wi, wd) in zip(got, want):
+            assert np.array_equal(gi, wi) and np.array_equal(gd, wd)
+    # k beyond the select kernel's 2048 and beyond the number of rows: every row comes back, in order
+    ids, dist = srch.exact_search_batch(batches[0][:3], n + 50, tensor_cores=False)
+    assert ids.shape == (3, n + 50) and bool((ids[:, n:] == -1).all()) and bool(np.isinf(dist[:, n:]).all())
+    assert sorted(ids[0, :n].tolist()) == list(range(n)) and bool((np.diff(dist[0, :n]) >= 0).all())
+    true_d = c_oracle.distances(S, batches[0][0].astype(np.float64))
+    assert np.abs(np.sort(true_d) - dist[0, :n]).max() < 1e-9
+    assert srch.exact_search_batch(batches[0][:2], 0, tensor_cores=False)[0].shape == (2, 0)
