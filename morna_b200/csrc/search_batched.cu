@@ -801,6 +801,7 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     } else {                 // ===== epilogue: thread = TMEM lane = query row of this CTA's half
         const int quarter = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
+        long long e_busy = 0;
         for (int t = pair; t < total_tiles; t += pairs) {
             const int m_pair = t % m_pairs, n_tile = t / m_pairs;
             const int row = m_pair * 2 * BM + (int)rank * BM + quarter * 32 + lane;
@@ -810,6 +811,7 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (p.mode == 1 && row_ok) thr = p.thr[row];
             if (p.relaxed_ns) mbar_wait_relaxed(tfull_bar(acc), acc_phase, (unsigned)p.relaxed_ns);
             else mbar_wait(tfull_bar(acc), acc_phase);
+            const long long e0 = p.debug ? clock64() : 0;
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
@@ -855,8 +857,10 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
             tc_fence_before();
             mbar_arrive_cluster(tempty_bar(acc), 0);       // the leader's MMA thread waits for both CTAs
+            if (p.debug) e_busy += clock64() - e0;
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
+        if (p.debug && warp == 2 && lane == 0) p.debug[blockIdx.x * 4 + 3] = e_busy;
         if (warp == 2 && lane == 0) *helper_stop = 1;      // this CTA's tiles are done: helpers finish their item and leave
     }
     tc_fence_before();

@@ -19,6 +19,9 @@ lib.morna_debug_gemm_counters(None)
 c = buf.view(148, 4).cpu()
 lead = c[::2]                                                 # leader CTAs issue the MMAs
 tot = lead[:, 2].float()
+tiles = (16 * ((N - 8192 + 255) // 256)) / 74.0
+print("epilogue warp 2 busy: %.0f k cycles per CTA = %.1f %% of the MMA thread's total, %.0f cycles per tile (a tile's MMAs: %.0f cycles)"
+      % (c[:, 3].float().mean() / 1e3, 100 * c[:, 3].float().mean() / tot.mean(), c[:, 3].float().mean() / tiles, tot.mean() / tiles))
 print("filter pass, per leader CTA: total %.0f k cycles; waiting for operand tiles %.1f %% (min %.1f, max %.1f), for a free accumulator %.1f %%"
       % (tot.mean() / 1e3, 100 * (lead[:, 0].float() / tot).mean(), 100 * (lead[:, 0].float() / tot).min(), 100 * (lead[:, 0].float() / tot).max(),
          100 * (lead[:, 1].float() / tot).mean()))
