@@ -526,6 +526,7 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct GemmParams {
     int32_t relaxed_ns;    // > 0: epilogue warps sleep this long between polls of the accumulator barrier (key 22)
+    int32_t dry_epilogue;  // key 23, timing experiments only: the filter epilogue finds the survivors but does not append them
     long long *debug;      // optional [gridDim.x][4] cycle counters of the MMA thread (full-barrier wait, accumulator wait, total) and the epilogue
     int32_t nq, n_begin, n_end, kblocks, m_blocks, n_tiles, mode, cap, id_base;
     float *pilot; int64_t pilot_ld;
@@ -703,8 +704,8 @@ __device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {
 // items of the previous batch (rr.queue != nullptr) from its queue -- the re-rank is a gather of candidate rows
 // through LSU + FP64 units the GEMM leaves idle.  They stop taking items when this CTA's epilogue has finished
 // its last tile; whatever is left in the queue is drained by rerank_warp_kernel afterwards.
-template <int kStages>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm2::THREADS_ALL, 1)
+template <int kStages, bool kHelpers>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHelpers ? gemm2::THREADS_ALL : gemm2::THREADS, 1)
 knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_s, GemmParams p,
                  const RerankParams rr) {
     using namespace gemm2;
@@ -720,7 +721,7 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     volatile uint32_t *tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     int *helper_lists = reinterpret_cast<int *>(smem_raw + (bars + 256u - smem_u32(smem_raw)));     // [HELPER_WARPS][1024]
-    volatile int *helper_stop = helper_lists + (blockDim.x > THREADS ? HELPER_WARPS * 1024 : 0);      // (no lists without helpers)
+    volatile int *helper_stop = helper_lists + (kHelpers ? HELPER_WARPS * 1024 : 0);                 // (no lists without helpers)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -796,7 +797,7 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
             if (p.debug) { p.debug[blockIdx.x * 4 + 0] = w_full; p.debug[blockIdx.x * 4 + 1] = w_acc; p.debug[blockIdx.x * 4 + 2] = clock64() - t_begin; }
         }
-    } else if (warp >= THREADS / 32) {     // ===== helper warps: re-rank items of the previous batch
+    } else if (kHelpers && warp >= THREADS / 32) {     // ===== helper warps: re-rank items of the previous batch
         if (rr.queue) rerank_warp_loop<8, 2>(rr, helper_lists + (warp - THREADS / 32) * 1024, lane, helper_stop);
     } else {                 // ===== epilogue: thread = TMEM lane = query row of this CTA's half
         const int quarter = warp & 3;
@@ -837,11 +838,13 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         }
                     }
                 } else {
+                    // one returning atomic per 32-column chunk and row with a survivor.  (Reserving a row's slots once per
+                    // tile -- two passes over the TMEM chunks -- was measured slower: 0.789 vs 0.767 ms per filter pass.)
                     uint32_t mask = 0;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         mask |= (uint32_t)(__uint_as_float(r[j]) >= thr && j < valid) << j;
-                    if (mask) {
+                    if (mask && !p.dry_epilogue) {                 // (dry: timing experiment without the appends; results invalid)
                         int at = atomicAdd(p.cand_cnt + row, __popc(mask));
                         float *cs = p.cand_score + (int64_t)row * p.cap;
                         int32_t *ci = p.cand_id + (int64_t)row * p.cap;
@@ -1149,6 +1152,7 @@ static int g_side_job = 0;         // key 17: 1 = side jobs on: helper warps in 
 static int g_rerank_pipe = 1;      // key 18: CTA-per-query re-rank with software-pipelined row loads
 static long long *g_gemm_debug = nullptr;   // morna_debug_gemm_counters: device buffer for the MMA thread's wait counters
 static int g_gemm_relaxed_ns = 0;  // key 22
+static int g_gemm_dry = 0;         // key 23
 static int g_carveout_hint = 0;    // key 19: ask for the maximum shared-memory carve-out on the batched path's kernels (co-residency across streams)
 static int g_rerank_oneshot = 1;   // key 20: CTA-per-query re-rank launched as one CTA per item (default; 0 = persistent grid): its CTAs retire one by
                                    // one, so the next batch's first kernels start under its tail (1.875 -> 1.834 ms per headline batch)
@@ -1166,7 +1170,10 @@ static int launch_knn_gemm(const CUtensorMap &tmap_q, const CUtensorMap &tmap_s,
         return MORNA_OK;
     }
     const int stages = g_gemm_stages == 4 ? 4 : 6;
-    auto kern = stages == 4 ? knn_gemm2_kernel<4> : knn_gemm2_kernel<6>;
+    // two builds of the kernel: with the helper warps (side job given) and without them -- the plain one is not held to the
+    // register budget of 448 threads
+    auto kern = side ? (stages == 4 ? knn_gemm2_kernel<4, true> : knn_gemm2_kernel<6, true>)
+                     : (stages == 4 ? knn_gemm2_kernel<4, false> : knn_gemm2_kernel<6, false>);
     const int smem = gemm2::smem_bytes(stages);
     int rca = ensure_dynamic_smem((const void *)kern, smem);
     if (rca != MORNA_OK) return rca;
@@ -1310,7 +1317,7 @@ static int score_impl(const void *hs, int64_t ld_h, const float *rho_max, int64_
     rc = make_tmap(&tmap_s, hs, (uint64_t)n, (uint64_t)ld_h, g_gemm_pair ? gemm2::BN_HALF : gemm::BN);
     if (rc != MORNA_OK) return rc;
     GemmParams gp{};
-    gp.debug = g_gemm_debug; gp.relaxed_ns = g_gemm_relaxed_ns;
+    gp.debug = g_gemm_debug; gp.relaxed_ns = g_gemm_relaxed_ns; gp.dry_epilogue = g_gemm_dry;
     gp.nq = (int32_t)nq; gp.kblocks = (int32_t)(ld_h / gemm::BK); gp.m_blocks = (int32_t)(w.nq_pad / gemm::BM);
     gp.cap = kCandCap; gp.id_base = id_base; gp.pilot = pilot; gp.pilot_ld = w.pilot_ld; gp.thr = thr;
     gp.cand_score = cand_score; gp.cand_id = cand_id; gp.cand_cnt = cand_cnt;
@@ -1716,6 +1723,7 @@ extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
     else if (key == 19) g_carveout_hint = value;
     else if (key == 20) g_rerank_oneshot = value;
     else if (key == 22) g_gemm_relaxed_ns = value;
+    else if (key == 23) g_gemm_dry = value;
 
     else return MORNA_ERR_INVALID_ARGUMENT;
     return MORNA_OK;
