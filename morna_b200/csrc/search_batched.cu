@@ -694,9 +694,9 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
     uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(addr));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
 
@@ -704,11 +704,15 @@ __device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {
 // items of the previous batch (rr.queue != nullptr) from its queue -- the re-rank is a gather of candidate rows
 // through LSU + FP64 units the GEMM leaves idle.  They stop taking items when this CTA's epilogue has finished
 // its last tile; whatever is left in the queue is drained by rerank_warp_kernel afterwards.
-template <int kStages, bool kHelpers>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHelpers ? gemm2::THREADS_ALL : gemm2::THREADS, 1)
-knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_s, GemmParams p,
-                 const RerankParams rr) {
+// kCluster = 2: the cluster is one CTA pair.  kCluster = 4 (experiment, key 0 = 2): two pairs that work on the same sample
+// tile for two different 256-query blocks; every CTA fetches a QUARTER of the sample tile and multicasts it to its
+// counterpart in the other pair, so the sample operand leaves L2 once per two pair-tiles (25 % fewer L2->SM bytes per flop);
+// a stage is free when BOTH pairs' MMAs have retired (two arrivals on every CTA's empty barrier).
+template <int kStages, bool kHelpers, int kCluster>
+__device__ __forceinline__ void
+knn_gemm2_body(const CUtensorMap &tmap_q, const CUtensorMap &tmap_s, const GemmParams &p, const RerankParams &rr) {
     using namespace gemm2;
+    constexpr bool kQuad = kCluster == 4;
     using namespace tc;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -724,14 +728,17 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     volatile int *helper_stop = helper_lists + (kHelpers ? HELPER_WARPS * 1024 : 0);                 // (no lists without helpers)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
+    const uint32_t crank = cluster_ctarank();               // rank in the cluster; the pair is (crank & ~1, crank | 1)
+    const uint32_t rank = crank & 1u;                       // rank within the pair
+    const uint32_t leader_rank = crank & ~1u;
+    const int pair_in_cluster = (int)(crank >> 1);
     const bool leader = rank == 0;
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_q);
         prefetch_tmap(&tmap_s);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), kQuad ? 2 : 1); }
         for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
         fence_barrier_init();
         *helper_stop = 0;
@@ -745,24 +752,31 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int pair = blockIdx.x >> 1, pairs = gridDim.x >> 1;
+    // work units: a pair (kCluster 2) or a cluster of two pairs (kCluster 4) owns one (query group, sample tile) at a time
+    const int pair = blockIdx.x / kCluster, pairs = gridDim.x / kCluster;
     const int m_pairs = (p.m_blocks + 1) >> 1;              // 256-row query blocks
-    const int total_tiles = m_pairs * p.n_tiles;
+    const int m_groups = kQuad ? (m_pairs + 1) >> 1 : m_pairs;
+    const int total_tiles = m_groups * p.n_tiles;
+    auto m_pair_of = [&](int t) { return kQuad ? 2 * (t % m_groups) + pair_in_cluster : t % m_groups; };
     if (warp == 0) {
-        if (lane == 0) {     // ===== TMA producer (both CTAs); bytes are counted on the leader's barrier
+        if (lane == 0) {     // ===== TMA producer (every CTA); bytes are counted on its pair leader's barrier
             int stage = 0; uint32_t phase = 0;
             for (int t = pair; t < total_tiles; t += pairs) {
-                const int m_pair = t % m_pairs, n_tile = t / m_pairs;
+                const int m_pair = m_pair_of(t), n_tile = t / m_groups;
                 const int row_q = m_pair * 2 * BM + (int)rank * BM;
-                const int row_s = p.n_begin + n_tile * BN + (int)rank * BN_HALF;
+                const int row_s = p.n_begin + n_tile * BN + (int)rank * BN_HALF + (kQuad ? pair_in_cluster * (BN_HALF / 2) : 0);
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     if (p.relaxed_ns > 1) mbar_wait_relaxed(empty_bar(stage), phase ^ 1, 20u);
                     else mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t a_dst = base + stage * STAGE_BYTES, b_dst = a_dst + A_BYTES;
-                    const uint32_t bar0 = mapa_rank0(full_bar(stage));
+                    const uint32_t bar0 = mapa_rank(full_bar(stage), leader_rank);
                     if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
                     tma_load_2d_pair(a_dst, &tmap_q, bar0, kb * BK, row_q);
-                    tma_load_2d_pair(b_dst, &tmap_s, bar0, kb * BK, row_s);
+                    if (kQuad)       // my quarter of the sample tile, to me and to my counterpart in the other pair
+                        tma_load_2d_pair_multicast(b_dst + pair_in_cluster * (B_BYTES / 2), &tmap_s, bar0, kb * BK, row_s,
+                                                   (uint16_t)((1u << crank) | (1u << (crank ^ 2u))));
+                    else
+                        tma_load_2d_pair(b_dst, &tmap_s, bar0, kb * BK, row_s);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -789,8 +803,8 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k)
                         umma_f16<2>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                    umma_commit_pair(empty_bar(stage), 3);          // frees the stage in both CTAs
-                    if (kb == p.kblocks - 1) umma_commit_pair(tfull_bar(acc), 3);
+                    umma_commit_pair(empty_bar(stage), kQuad ? 0xF : 0x3);     // frees the stage in every CTA that TMA writes for it
+                    if (kb == p.kblocks - 1) umma_commit_pair(tfull_bar(acc), (uint16_t)(0x3u << leader_rank));
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
@@ -804,7 +818,7 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         int acc = 0; uint32_t acc_phase = 0;
         long long e_busy = 0;
         for (int t = pair; t < total_tiles; t += pairs) {
-            const int m_pair = t % m_pairs, n_tile = t / m_pairs;
+            const int m_pair = m_pair_of(t), n_tile = t / m_groups;
             const int row = m_pair * 2 * BM + (int)rank * BM + quarter * 32 + lane;
             const bool row_ok = row < p.nq;
             const int col_tile = p.n_begin + n_tile * BN;
@@ -859,7 +873,7 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 }
             }
             tc_fence_before();
-            mbar_arrive_cluster(tempty_bar(acc), 0);       // the leader's MMA thread waits for both CTAs
+            mbar_arrive_cluster(tempty_bar(acc), leader_rank);       // the pair leader's MMA thread waits for both CTAs
             if (p.debug) e_busy += clock64() - e0;
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
@@ -869,6 +883,20 @@ knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     tc_fence_before();
     cluster_sync_all();
     if (warp == 2) tmem_dealloc<2>(tmem_base, TMEM_COLS);
+}
+
+template <int kStages, bool kHelpers>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHelpers ? gemm2::THREADS_ALL : gemm2::THREADS, 1)
+knn_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_s, GemmParams p,
+                 const RerankParams rr) {
+    knn_gemm2_body<kStages, kHelpers, 2>(tmap_q, tmap_s, p, rr);
+}
+
+template <int kStages>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(gemm2::THREADS, 1)
+knn_gemm4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_s, GemmParams p,
+                 const RerankParams rr) {
+    knn_gemm2_body<kStages, false, 4>(tmap_q, tmap_s, p, rr);
 }
 
 // ------------------------------------------------------------------ k-th largest + filter
@@ -1169,6 +1197,23 @@ static int launch_knn_gemm(const CUtensorMap &tmap_q, const CUtensorMap &tmap_s,
         MORNA_LAUNCH_CHECK();
         return MORNA_OK;
     }
+    if (g_gemm_pair == 2 && !side && (gp.m_blocks % 4) == 0) {          // experiment: clusters of two pairs, multicast sample tile
+        auto kern4 = knn_gemm4_kernel<4>;
+        const int smem4 = gemm2::smem_bytes(4) - gemm2::HELPER_BYTES + 16;
+        int rca = ensure_dynamic_smem((const void *)kern4, smem4);
+        if (rca != MORNA_OK) return rca;
+        int tiles4 = (gp.m_blocks / 4) * gp.n_tiles;
+        int clusters = 0;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(4 * (sm_count_b() / 4)); cfg.blockDim = dim3(gemm2::THREADS); cfg.dynamicSmemBytes = smem4; cfg.stream = s;
+        if (cudaOccupancyMaxActiveClusters(&clusters, kern4, &cfg) != cudaSuccess || clusters < 1) { cudaGetLastError(); clusters = sm_count_b() / 4; }
+        if (clusters > sm_count_b() / 4) clusters = sm_count_b() / 4;
+        if (tiles4 < clusters) clusters = tiles4;
+        RerankParams none{};
+        kern4<<<4 * clusters, gemm2::THREADS, smem4, s>>>(tmap_q, tmap_s, gp, none);
+        MORNA_LAUNCH_CHECK();
+        return MORNA_OK;
+    }
     const int stages = g_gemm_stages == 4 ? 4 : 6;
     // two builds of the kernel: with the helper warps (side job given) and without them -- the plain one is not held to the
     // register budget of 448 threads
@@ -1314,7 +1359,8 @@ static int score_impl(const void *hs, int64_t ld_h, const float *rho_max, int64_
     CUtensorMap tmap_q, tmap_s;
     int rc = make_tmap(&tmap_q, hq, (uint64_t)w.nq_pad, (uint64_t)ld_h, gemm::BM);
     if (rc != MORNA_OK) return rc;
-    rc = make_tmap(&tmap_s, hs, (uint64_t)n, (uint64_t)ld_h, g_gemm_pair ? gemm2::BN_HALF : gemm::BN);
+    rc = make_tmap(&tmap_s, hs, (uint64_t)n, (uint64_t)ld_h,
+                   g_gemm_pair == 2 && !side_ptr && (w.nq_pad / gemm::BM) % 4 == 0 ? gemm2::BN_HALF / 2 : g_gemm_pair ? gemm2::BN_HALF : gemm::BN);
     if (rc != MORNA_OK) return rc;
     GemmParams gp{};
     gp.debug = g_gemm_debug; gp.relaxed_ns = g_gemm_relaxed_ns; gp.dry_epilogue = g_gemm_dry;
@@ -1685,7 +1731,8 @@ extern "C" int morna_debug_tensor_scores(const void *hs, int64_t ld_h, const flo
     CUtensorMap tmap_q, tmap_s;
     int rc = make_tmap(&tmap_q, hq, (uint64_t)w.nq_pad, (uint64_t)ld_h, gemm::BM);
     if (rc != MORNA_OK) return rc;
-    rc = make_tmap(&tmap_s, hs, (uint64_t)n, (uint64_t)ld_h, g_gemm_pair ? gemm2::BN_HALF : gemm::BN);
+    rc = make_tmap(&tmap_s, hs, (uint64_t)n, (uint64_t)ld_h,
+                   g_gemm_pair == 2 && (w.nq_pad / gemm::BM) % 4 == 0 ? gemm2::BN_HALF / 2 : g_gemm_pair ? gemm2::BN_HALF : gemm::BN);
     if (rc != MORNA_OK) return rc;
     GemmParams gp{};
     gp.nq = (int32_t)nq; gp.kblocks = (int32_t)(ld_h / gemm::BK); gp.m_blocks = (int32_t)(w.nq_pad / gemm::BM);
@@ -1702,7 +1749,7 @@ namespace morna { void set_single_tma(int v); void set_acc_pipelined(int v); voi
 extern "C" int morna_debug_gemm_counters(void *buffer) { g_gemm_debug = (long long *)buffer; return MORNA_OK; }
 
 extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
-    if (key == 0) g_gemm_pair = value ? 1 : 0;
+    if (key == 0) g_gemm_pair = value == 2 ? 2 : (value ? 1 : 0);
     else if (key == 3) morna::set_single_tma(value);
     else if (key == 4) morna::set_acc_pipelined(value);
     else if (key == 1) g_gemm_stages = value;

@@ -93,6 +93,17 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_leader), "r"(c0), "r"(c1) : "memory");
 }
 
+// The pair flavour with multicast: the tile lands at the same shared-memory offset in every CTA of `cta_mask` (cluster
+// ranks), and each destination's bytes are counted on the barrier at bar's offset in the destination's pair, in the CTA
+// whose rank parity is that of the CTA `bar_leader` points to (the even, MMA-issuing CTA of each pair).
+__device__ __forceinline__ void tma_load_2d_pair_multicast(uint32_t dst, const CUtensorMap *m, uint32_t bar_leader, int32_t c0,
+                                                           int32_t c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_leader), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05
 template <int kCtaGroup>
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {

@@ -96,15 +96,16 @@ def test_batched_equals_exact_scan_bit_for_bit(n, d, nq, k):
     print("stats", srch.last_stats, "per query survivors %.1f final %.1f" % (srch.last_stats[1] / nq, srch.last_stats[2] / nq))
 
 
-@pytest.mark.parametrize("pair,stages", [(1, 6), (1, 4), (0, 4)])
+@pytest.mark.parametrize("pair,stages", [(1, 6), (1, 4), (0, 4), (2, 4)])
 def test_gemm_variants_agree(pair, stages):
-    """CTA-pair (cta_group::2) and single-CTA GEMM variants give the same exact results."""
+    """CTA-pair (cta_group::2), single-CTA and cluster-of-two-pairs (TMA multicast of the sample tile) GEMM variants give
+    the same exact results."""
     from morna_b200 import _lib
     lib = _lib.load()
     try:
         assert lib.morna_debug_set_tuning(0, pair) == 0 and lib.morna_debug_set_tuning(1, stages) == 0
         rng = np.random.default_rng(77)
-        n, d, nq, k = 17000, 1000, 700, 64
+        n, d, nq, k = 17000, 1000, 700 if pair != 2 else 1024, 64      # (the cluster variant needs a multiple of 512 queries)
         S = rng.standard_normal((n, d)).astype(np.float32)
         srch = make_search(S)
         Q = S[rng.permutation(n)[:nq]].astype(np.float64) + 0.02 * rng.standard_normal((nq, d))
