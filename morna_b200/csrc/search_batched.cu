@@ -1131,6 +1131,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+static int g_tmap_promotion = 3;   // key 24: L2 promotion of the operand tensor maps (0 none, 1 64 B, 2 128 B, 3 256 B)
+
 static EncodeTiledFn encode_tiled_fn() {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
@@ -1151,9 +1153,11 @@ static int make_tmap(CUtensorMap *map, const void *ptr, uint64_t rows, uint64_t 
     cuuint64_t strides[1] = {ld_h * sizeof(__half)};
     cuuint32_t box[2] = {(cuuint32_t)gemm::BK, box_rows};
     cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapL2promotion promo = g_tmap_promotion == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                        : g_tmap_promotion == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                        : g_tmap_promotion == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return MORNA_ERR_CUDA; }
     return MORNA_OK;
 }
@@ -1771,6 +1775,7 @@ extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
     else if (key == 20) g_rerank_oneshot = value;
     else if (key == 22) g_gemm_relaxed_ns = value;
     else if (key == 23) g_gemm_dry = value;
+    else if (key == 24) g_tmap_promotion = value;
 
     else return MORNA_ERR_INVALID_ARGUMENT;
     return MORNA_OK;

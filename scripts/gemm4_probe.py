@@ -14,8 +14,8 @@ events, arr = make_phase_events()
 buf = torch.zeros(148 * 4, dtype=torch.int64, device="cuda")
 ref = None
 for rnd in range(2):
-    for variant in (1, 2):
-        lib.morna_debug_set_tuning(0, variant)
+    for variant, promo, stages in ((1, 3, 4), (1, 2, 4), (1, 0, 4), (1, 3, 6), (2, 3, 4)):
+        lib.morna_debug_set_tuning(0, variant); lib.morna_debug_set_tuning(24, promo); lib.morna_debug_set_tuning(1, stages)
         for _ in range(3): s.batched_search_device(q, K, phase_events=arr)
         torch.cuda.synchronize(); time.sleep(0.3)
         acc = [0.0] * 6
@@ -26,6 +26,6 @@ for rnd in range(2):
         buf.zero_()
         lib.morna_debug_gemm_counters(_lib.dev_ptr(buf)); s.batched_search_device(q, K); torch.cuda.synchronize(); lib.morna_debug_gemm_counters(None)
         c = buf.view(148, 4).cpu()[::2].float(); c = c[c[:, 2] > 0]
-        print("GEMM variant %d: pilot GEMM %.3f ms, filter GEMM %.3f ms | %d MMA threads, %.0f k cycles, %.1f %% waiting for tiles | same results %s"
-              % (variant, acc[1], acc[3], c.shape[0], c[:, 2].mean() / 1e3, 100 * (c[:, 0] / c[:, 2]).mean(), torch.equal(ids, ref[0]) and torch.equal(d, ref[1])), flush=True)
-lib.morna_debug_set_tuning(0, 1)
+        print("GEMM variant %d, L2 promotion %d, %d stages: pilot GEMM %.3f ms, filter GEMM %.3f ms | %d MMA threads, %.0f k cycles, %.1f %% waiting for tiles | same results %s"
+              % (variant, promo, stages, acc[1], acc[3], c.shape[0], c[:, 2].mean() / 1e3, 100 * (c[:, 0] / c[:, 2]).mean(), torch.equal(ids, ref[0]) and torch.equal(d, ref[1])), flush=True)
+lib.morna_debug_set_tuning(0, 1); lib.morna_debug_set_tuning(24, 3); lib.morna_debug_set_tuning(1, 4)
