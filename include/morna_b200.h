@@ -50,6 +50,9 @@ const char *morna_status_string(int status);
 int morna_last_cuda_error(void);
 /* number of kernels this library has launched from the calling process (monotone counter) */
 int64_t morna_kernel_launch_count(void);
+/* A caller that captured calls of this library into a CUDA graph reports every replay here (kernels = the launches the
+ * capture counted), so the counter keeps meaning "kernels of this library that ran". */
+int morna_note_graph_replay(int64_t kernels);
 /* sm count / compute capability of the current device */
 int morna_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor);
 

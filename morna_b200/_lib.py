@@ -37,6 +37,7 @@ _SIGNATURES = {
     "morna_status_string": (ctypes.c_char_p, [ctypes.c_int]),
     "morna_last_cuda_error": (ctypes.c_int, []),
     "morna_kernel_launch_count": (_c_i64, []),
+    "morna_note_graph_replay": (ctypes.c_int, [_c_i64]),
     "morna_device_info": (ctypes.c_int, [_c_vp, _c_vp, _c_vp]),
     "morna_hash_junctions": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp]),
     "morna_idf_host": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp]),

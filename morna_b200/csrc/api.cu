@@ -60,6 +60,12 @@ extern "C" int morna_last_cuda_error(void) { return morna::g_last_cuda_error; }
 
 extern "C" int64_t morna_kernel_launch_count(void) { return (int64_t)morna::g_launches.load(); }
 
+extern "C" int morna_note_graph_replay(int64_t kernels) {
+    if (kernels < 0) return MORNA_ERR_INVALID_ARGUMENT;
+    morna::g_launches.fetch_add(kernels, std::memory_order_relaxed);
+    return MORNA_OK;
+}
+
 extern "C" int morna_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor) {
     int dev = 0, v = 0;
     MORNA_CUDA_TRY(cudaGetDevice(&dev));

@@ -702,6 +702,7 @@ class BatchPipeline(object):
         key = buffers()
         if self.use_graphs and getattr(sl, "graph_key", None) == key:
             sl.graph.replay()
+            self.search.lib.morna_note_graph_replay(sl.graph_launches)     # the library's launch counter counts kernels that ran
         else:
             seen = getattr(sl, "seen_key", None)
             sl.graph_key = None
@@ -710,6 +711,7 @@ class BatchPipeline(object):
                 # garbage collector and empty the allocator cache first -- a stall of several batch times.  Nothing is
                 # allocated between the two calls (every buffer of the step already exists).
                 graph = torch.cuda.CUDAGraph()
+                launches0 = _lib.launch_count()
                 graph.capture_begin(capture_error_mode="thread_local")
                 try:
                     self._score(sl, None)
@@ -717,6 +719,7 @@ class BatchPipeline(object):
                 finally:
                     graph.capture_end()
                 sl.graph, sl.graph_key = graph, key
+                sl.graph_launches = _lib.launch_count() - launches0      # counted once while capturing: stands for the replay below
                 graph.replay()
             else:
                 self._score(sl, None)
