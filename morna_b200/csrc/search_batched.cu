@@ -76,10 +76,9 @@ prep_queries_kernel(const double *__restrict__ queries, int64_t nq, int64_t nq_p
         }
         const double *q = queries + row * q_ld;
         const bool vec_ok = ((q_ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(queries) & 15) == 0);
-        double acc = 0.0;
-        bool huge = false;                               // the re-rank stages q * 2^896 (f32_scaled_f64)
-        for (int c = lane; 4 * c < dim; c += 32) {       // same lane/chunk partition as the scan
-            double a[4];
+        // chunk c of the row as four doubles (zeros past the end); kPrepInFlight chunks are loaded before any is used:
+        // one warp per query leaves the loop latency-bound otherwise
+        auto load_chunk = [&](int c, double (&a)[4]) {
             if (vec_ok && 4 * c + 3 < dim) {
                 const double2 lo = *reinterpret_cast<const double2 *>(q + 4 * c), hi = *reinterpret_cast<const double2 *>(q + 4 * c + 2);
                 a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
@@ -87,10 +86,21 @@ prep_queries_kernel(const double *__restrict__ queries, int64_t nq, int64_t nq_p
 #pragma unroll
                 for (int t = 0; t < 4; ++t) a[t] = (4 * c + t < dim) ? q[4 * c + t] : 0.0;
             }
+        };
+        constexpr int kPrepInFlight = 4;
+        double acc = 0.0;
+        bool huge = false;                               // the re-rank stages q * 2^896 (f32_scaled_f64)
+        for (int c0 = lane; 4 * c0 < dim; c0 += 32 * kPrepInFlight) {       // same lane/chunk partition and order as the scan
+            double a[kPrepInFlight][4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                huge |= !(fabs(a[t]) < kScaledQueryMax);
-                acc = fma(a[t], a[t], acc);
+            for (int u = 0; u < kPrepInFlight; ++u) load_chunk(c0 + 32 * u, a[u]);      // chunks past the row are zeros: fma(0, 0, acc) == acc
+#pragma unroll
+            for (int u = 0; u < kPrepInFlight; ++u) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    huge |= !(fabs(a[u][t]) < kScaledQueryMax);
+                    acc = fma(a[u][t], a[u][t], acc);
+                }
             }
         }
         acc = warp_sum(acc);
@@ -101,27 +111,27 @@ prep_queries_kernel(const double *__restrict__ queries, int64_t nq, int64_t nq_p
         const double norm = sqrt(acc);
         const double inv = norm > 0.0 ? 1.0 / norm : 0.0;
         double res = 0.0;
-        for (int c = lane; c < chunks_h; c += 32) {
-            __half h[4];
-            double a[4];
-            if (vec_ok && 4 * c + 3 < dim) {
-                const double2 lo = *reinterpret_cast<const double2 *>(q + 4 * c), hi = *reinterpret_cast<const double2 *>(q + 4 * c + 2);
-                a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
-            } else {
+        for (int c0 = lane; c0 < chunks_h; c0 += 32 * kPrepInFlight) {
+            double a[kPrepInFlight][4];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) a[t] = (4 * c + t < dim) ? q[4 * c + t] : 0.0;
-            }
+            for (int u = 0; u < kPrepInFlight; ++u) load_chunk(c0 + 32 * u, a[u]);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                double x = a[t] * inv;
-                h[t] = __float2half_rn((float)x);
-                double r = x - (double)__half2float(h[t]);
-                res = fma(r, r, res);
+            for (int u = 0; u < kPrepInFlight; ++u) {
+                const int c = c0 + 32 * u;
+                if (c >= chunks_h) break;
+                __half h[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    double x = a[u][t] * inv;
+                    h[t] = __float2half_rn((float)x);
+                    double r = x - (double)__half2float(h[t]);
+                    res = fma(r, r, res);
+                }
+                uint2 packed;
+                packed.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+                packed.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+                dst[c] = packed;
             }
-            uint2 packed;
-            packed.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
-            packed.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
-            dst[c] = packed;
         }
         res = warp_sum(res);
         if (lane == 0) {
@@ -937,8 +947,9 @@ __device__ __forceinline__ uint32_t warp_kth_largest(const uint32_t (&key)[kItem
     return best;
 }
 
+constexpr int kCandCapConst = 4096;                   // = kCandCap below
 constexpr int kKwWarps = 8, kKwSlots = 32;            // one warp per query; 32 survivors per lane
-constexpr int kKwSmem = kKwWarps * 2 * 32 * kKwSlots * (int)sizeof(uint32_t);   // 64 KB
+constexpr int kKwSmem = kKwWarps * 32 * kKwSlots * (int)(sizeof(uint32_t) + sizeof(uint16_t));   // 48 KB: four CTAs per SM, 4096 queries resident at once
 
 // One WARP per query (8 queries per CTA, no block barriers).
 //   kMode 1 (pilot) : input = dumped pilot scores -> thr[q] and the pilot's survivors start the candidate list
@@ -962,8 +973,9 @@ kth_warp_kernel(KthParams p, int nq) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = blockIdx.x * kKwWarps + warp;
     if (q >= nq) return;
-    uint32_t *lkey = kw_smem + warp * 2 * 32 * kKwSlots;          // [slot][lane]
-    uint32_t *lidx = lkey + 32 * kKwSlots;
+    uint32_t *lkey = kw_smem + warp * 32 * kKwSlots;              // [slot][lane]
+    uint16_t *lidx = reinterpret_cast<uint16_t *>(kw_smem + kKwWarps * 32 * kKwSlots) + warp * 32 * kKwSlots;   // entry index < 8192
+    static_assert(kKthMax <= 65536 && kCandCapConst <= 65536, "entry indices are kept in 16 bits");
     int count;
     if (kPilot) count = p.n0;
     else {
@@ -1019,7 +1031,7 @@ kth_warp_kernel(KthParams p, int nq) {
                     const int idx = 4 * g + t;
                     const uint32_t key = float_key(vv[t]);
                     if (idx < count && key >= pivot) {
-                        if (mine < kKwSlots) { lkey[mine * 32 + lane] = key; lidx[mine * 32 + lane] = idx; }
+                        if (mine < kKwSlots) { lkey[mine * 32 + lane] = key; lidx[mine * 32 + lane] = (uint16_t)idx; }
                         else overflowed = true;
                         ++mine;
                     }
@@ -1164,7 +1176,7 @@ static int make_tmap(CUtensorMap *map, const void *ptr, uint64_t rows, uint64_t 
 
 static int sm_count_b() { return sm_count_current(); }
 
-constexpr int kCandCap = 4096, kFinCap = 1024, kPilotMax = kKthMax;
+constexpr int kCandCap = kCandCapConst, kFinCap = 1024, kPilotMax = kKthMax;
 constexpr int64_t kBatchedMaxRows = (int64_t)1 << 24;      // rows one call may score (ids are int32; TMA row coordinate)
 
 // tuning knobs for experiments (morna_debug_set_tuning): GEMM variant and pipeline depth
