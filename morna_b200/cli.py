@@ -90,7 +90,22 @@ def build_parser():
                               help="be talkative")
     index_parser.add_argument("-m", "--metafile", metavar="<file>", type=str, required=False, default=None,
                               help="metadata file: sample id then keywords per line; stored in <basename>.meta.mor for search -m")
+    index_parser.add_argument("--no-junction-shards", action="store_const", const=True, default=False,
+                              help="do not write the <basename>.shXX.junc.mor shards (only `junctions` reads them)")
     add_search_parameters(search_parser)
+    junctions_parser = subs.add_parser("junctions", help="extracts the junctions of a query's nearest neighbors")
+    add_search_parameters(junctions_parser)                      # morna.py:1023-1054
+    junctions_parser.add_argument("-i", "--index", metavar="<idx>", type=str, required=True,
+                                  help="index basename or directory of the aligner (kept for compatibility)")
+    junctions_parser.add_argument("-p1", "--pass1-sam", metavar="<sam>", type=str, required=False, default="pass1.sam",
+                                  help="filename for first pass alignment file output by aligner")
+    junctions_parser.add_argument("--junction-filter", type=str, required=False, default=".05,5",
+                                  help="retain junctions found in at least {first part} of the result samples, or "
+                                       "with at least {second part} coverage in any one result sample")
+    junctions_parser.add_argument("--junction-file", type=str, metavar="<gz>", required=True,
+                                  help="gzipped file with junction rows in the order of the file the index was made from")
+    junctions_parser.add_argument("-sf", "--splicefile", type=str, metavar="<file>", required=True,
+                                  help="output intropolis-like file with the retained junctions")
     return parser
 
 
@@ -104,7 +119,8 @@ def main(argv=None, stdin=None, stdout=None, stderr=None):
     if args.subparser_name == "index":
         from .index import go_index
         go_index(args.intropolis, args.basename, args.features, args.n_trees, args.sample_count,
-                 args.sample_threshold, args.buffer_size, args.verbose, args.metafile, out=stdout)
+                 args.sample_threshold, args.buffer_size, args.verbose, args.metafile, out=stdout,
+                 junction_shards=not args.no_junction_shards)
         return 0
 
     from . import parse
@@ -112,6 +128,10 @@ def main(argv=None, stdin=None, stdout=None, stderr=None):
     if args.convergence_backoff:
         stderr.write("convergence back-off is not supported (see README of the reference: non-functional)\n")
         return 2
+    opened = None
+    if args.subparser_name == "junctions":                      # morna.py:1351-1353
+        args.format = "sam"
+        stdin = opened = open(args.pass1_sam)
     searcher = MornaSearch(basename=args.basename)
     if args.query_id is not None:                               # morna.py:1358-1365
         results = searcher.search_member_n(args.query_id, args.results, args.search_k,
@@ -143,6 +163,10 @@ def main(argv=None, stdin=None, stdout=None, stderr=None):
     else:
         results = searcher.search_nn(args.results, args.search_k, include_distances=args.distances, meta_db=args.metadata)
     results_output(results, stdout)
+    if args.subparser_name == "junctions":                      # :1486-1632
+        from .junctions import go_junctions
+        go_junctions(args, searcher, results, stdout, stderr)
+        opened.close()
     return 0
 
 

@@ -5,7 +5,8 @@ Same constructor arguments, same ``add_junction`` / ``build`` / ``save`` surface
 same errors.  ``add_junction`` only records the row (threshold test, cumulative
 frequency, key bytes); ``build`` ships the rows to the device once as binary CSR
 and runs hash -> first-seen ids -> order-faithful scatter-add -> float32 store.
-Annoy's forest (``n_trees``) and the sqlite side files are out of scope.
+Annoy's forest (``n_trees``) is not built; the junctions-by-sample shards are written by
+``morna_b200.junctions`` when ``junction_shards`` is set, the metadata table by ``files.write_meta``.
 """
 import numpy as np
 import torch
@@ -25,7 +26,7 @@ def round_up(x, m):
 
 class MornaIndex(object):
     def __init__(self, sample_count, basename, dim=3000, sample_threshold=100,
-                 metafile=None, buffer_size=1024, device=None, store_skipped_rows=False):
+                 metafile=None, buffer_size=1024, device=None, store_skipped_rows=False, junction_shards=False):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
@@ -41,6 +42,11 @@ class MornaIndex(object):
         self.buffer_size = buffer_size
         self.junc_id = -1                                # :215
         self._rows = RowBatch()
+        self._shards = None          # junctions-by-sample shards (morna.py:200-219), written by save()
+        if junction_shards:
+            from .junctions import ShardRecorder, remove_shards
+            remove_shards(basename)
+            self._shards = ShardRecorder(basename, buffer_size, self.device)
         self._store_skipped = store_skipped_rows   # ship under-threshold rows too (kernel tests)
         self._pass = []
         self._running_freq = []
@@ -53,6 +59,8 @@ class MornaIndex(object):
         """morna.py:344-388: threshold filter, cumulative frequency; the hash, idf and
         per-pair scatter-add happen on the device in build()."""
         self.junc_id += 1
+        if self._shards is not None:                     # :359, before the threshold
+            self._shards.add_row(self.junc_id, samples, coverages)
         n = len(samples)
         if n < self.sample_threshold:                    # :361-363
             self.skipped += 1
@@ -109,9 +117,11 @@ class MornaIndex(object):
             freq = freqs.get(key, 0) + int(lens[i])
             freqs[key] = freq
             running[i] = freq
+        p0, p1 = int(row_off[r0]), int(row_off[r1])
+        if self._shards is not None:
+            self._shards.add_rows(self.junc_id + 1, lens, sample[p0:p1], cov[p0:p1])
         self.junc_id += r1 - r0
         self.skipped += int((~passing).sum())
-        p0, p1 = int(row_off[r0]), int(row_off[r1])
         if seen_samples is not None and p1 > p0:         # canonical integers: distinct strings == distinct values
             seen_samples.update(np.unique(sample[p0:p1]).astype(str).tolist())
         if self._store_skipped or passing.all():
@@ -231,19 +241,21 @@ class MornaIndex(object):
         files.write_stats(basename, self.sample_count, self.new_internal_id, self.dim)
         files.write_freq(basename, self.sample_frequencies)
         files.write_map(basename, self.internal_id_map)
+        if self._shards is not None:                       # morna.py:457-488
+            self._shards.write()
         if self.metafile:                                  # morna.py:494-520
             files.write_meta(basename, self.metafile)
 
 
 def go_index(intropolis, basename, features, n_trees, sample_count, sample_threshold, buffer_size,
-             verbose, metafile, out=None):
-    """morna.py:824-865."""
+             verbose, metafile, out=None, junction_shards=True):
+    """morna.py:824-865.  ``junction_shards=False`` skips the junctions-by-sample shards (only ``junctions`` reads them)."""
     import sys
     out = out or sys.stdout
     from . import parse
     seen = None if sample_count else set()              # one pass serves count_samples too (morna.py:789-822)
     index = MornaIndex(sample_count or 0, basename, dim=features, sample_threshold=sample_threshold,
-                       metafile=metafile, buffer_size=buffer_size)
+                       metafile=metafile, buffer_size=buffer_size, junction_shards=junction_shards)
     done = 0
     with parse.open_intropolis_binary(intropolis) as fh:
         for block in parse.read_blocks(fh):

@@ -452,9 +452,13 @@ def test_index_from_text_blocks_equals_index_from_python_rows(tmp_path):
     path = str(tmp_path / "rows.tsv.gz")
     with gzip.open(path, "wb") as fh:
         fh.write(text)
-    c = go_index(path, str(tmp_path / "idx"), 200, None, None, 4, 1024, False, None, out=io.StringIO())
+    c = go_index(path, str(tmp_path / "idx"), 200, None, None, 4, 1024, False, None, out=io.StringIO(), junction_shards=False)
     assert c.sample_count == n_samples
     assert np.array_equal(c.matrix_f32(), a.matrix_f32())
+    # with the junctions-by-sample shards on (the command's default) the row with fewer coverages than samples stops the
+    # run as it stops the reference: update_junction_dbs reads coverages[i] for every sample (morna.py:269)
+    with pytest.raises(IndexError):
+        go_index(path, str(tmp_path / "idx2"), 200, None, None, 4, 1024, False, None, out=io.StringIO())
 
 
 def test_index_build_properties_at_scale():
