@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MORNA_ABI_VERSION 2
+#define MORNA_ABI_VERSION 3
 
 enum {
     MORNA_OK = 0,
@@ -82,12 +82,15 @@ int morna_idf_host(const int64_t *running_freq, const uint8_t *pass, int64_t n_r
  *   row_off      [dev] int64[J+1] CSR offsets into sample[]
  *   pass         [dev] uint8[J]   1 if len(samples) >= sample_threshold (morna.py:361)
  *   sample       [dev] int32[nnz] sample ids, each in [0, max_sample_id]
+ *   distinct_samples   number of distinct sample ids in the input if the caller counted them (count_samples,
+ *                morna.py:789-822; an over-estimate is safe, an under-estimate is not), else 0.  Once that many ids have
+ *                been met the remaining rows are not read: first-seen ids depend on first occurrences only.
  *   id_of_sample [dev] int32[max_sample_id+1] out: internal id or -1
  *   n_kept       [dev] int32[1]   out: number of ids assigned (.stats.mor line 2)
  */
 size_t morna_assign_internal_ids_workspace_bytes(int64_t n_rows, int64_t nnz, int32_t max_sample_id);
 int morna_assign_internal_ids(const int64_t *row_off, const uint8_t *pass, int64_t n_rows,
-                              const int32_t *sample, int64_t nnz, int32_t max_sample_id,
+                              const int32_t *sample, int64_t nnz, int32_t max_sample_id, int64_t distinct_samples,
                               int32_t *id_of_sample, int32_t *n_kept,
                               void *workspace, size_t workspace_bytes, void *stream);
 

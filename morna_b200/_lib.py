@@ -21,7 +21,7 @@ ERR_NO_SAMPLES = -5
 ERR_CAPACITY = -6
 
 _c_i32, _c_i64, _c_sz, _c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t, ctypes.c_void_p
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class RerankJob(ctypes.Structure):
@@ -42,7 +42,7 @@ _SIGNATURES = {
     "morna_hash_junctions": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp]),
     "morna_idf_host": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp]),
     "morna_assign_internal_ids_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_i32]),
-    "morna_assign_internal_ids": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_i32, _c_vp, _c_vp,
+    "morna_assign_internal_ids": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_i32, _c_i64, _c_vp, _c_vp,
                                                  _c_vp, _c_sz, _c_vp]),
     "morna_tokenize_count": (ctypes.c_int, [_c_vp, _c_sz, _c_i32, _c_vp, _c_vp, _c_vp]),
     "morna_tokenize_fill": (ctypes.c_int, [_c_vp, _c_sz, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),

@@ -178,7 +178,7 @@ template <int R, int U>
 __global__ void __launch_bounds__(kS1Threads, 2)
 scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict__ pp, int64_t n, int64_t ld,
                      int32_t dim, int32_t id_base, const double *__restrict__ query, int32_t k, int64_t rows_per_warp,
-                     double *__restrict__ dist, float *__restrict__ sel, unsigned int *__restrict__ hist,
+                     int32_t prefetch_bytes, int32_t prefetch_rows, double *__restrict__ dist, float *__restrict__ sel, unsigned int *__restrict__ hist,
                      int32_t *__restrict__ lists, SingleWs *ctl,
                      int32_t *__restrict__ out_ids, double *__restrict__ out_dist, int32_t *__restrict__ fallback_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -197,6 +197,21 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
     const int chunks = (int)(ld >> 2);
     if (tid == 0) s_huge = 0;
     if (blockIdx.x == 0 && tid == 0) ctl->stamp[0] = global_ns();
+    if (prefetch_bytes > 0) {
+        // The query staging and the qq sum below take ~3 us in which no row is read.  Pull this warp's first-pass rows
+        // into L2 meanwhile (no registers held): HBM starts streaming at once.  Measured (scripts/single_prefetch_sweep.py,
+        // 21,504 x 3000): 59.0 -> 55.5 us per query with whole first-pass rows (half the matrix = the L2's size); more
+        // rows, or prefetching every next pass from inside the loop, overflow L2 and cost 2-20 us.
+        const int64_t gw0 = (int64_t)blockIdx.x * kS1Warps + warp;
+        const int64_t first = gw0 * rows_per_warp;
+        const int lines = min(prefetch_bytes, (int)(ld * 4)) >> 7;            // 128-byte lines per row
+        const int rows_ahead = prefetch_rows > 0 ? prefetch_rows : R;
+        for (int u = 0; u < rows_ahead && u < rows_per_warp; ++u) {
+            if (first + u >= n) break;
+            const char *row = reinterpret_cast<const char *>(vectors + (first + u) * ld);
+            for (int l = lane; l < lines; l += 32) asm volatile("prefetch.global.L2 [%0];" :: "l"(row + 128 * l));
+        }
+    }
     __syncthreads();
     {
         bool huge = false;
@@ -420,6 +435,10 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
     if (tid == 0) ctl->stamp[3] = global_ns();
 }
 
+static int g_single_prefetch = 1 << 20;   // morna_debug_set_tuning key 27: bytes (clamped to the row) of each first-pass row pulled into L2 before the query is staged
+void set_single_prefetch(int v) { g_single_prefetch = v >= 0 ? v : 0; }
+static int g_single_prefetch_rows = 0;   // key 28: rows of the warp's share covered by that prefetch (0 = the first pass)
+void set_single_prefetch_rows(int v) { g_single_prefetch_rows = v >= 0 ? v : 0; }
 static int g_single_rows = 0;     // morna_debug_set_tuning key 3: rows per warp pass (0 = automatic)
 void set_single_tma(int v) { g_single_rows = v; }
 
@@ -445,7 +464,7 @@ static int launch_scan64(unsigned grid, size_t smem, cudaStream_t s, const float
                          double *dist, float *sel, unsigned int *hist, int32_t *lists, SingleWs *ctl, int32_t *out_ids, double *out_dist, int32_t *fallback) {
     { int rca = ensure_dynamic_smem((const void *)scan64_select_kernel<R, U>, smem); if (rca != MORNA_OK) return rca; }
     scan64_select_kernel<R, U><<<grid, kS1Threads, smem, s>>>(vectors, pp, n, ld, dim, id_base, query, k, rows_per_warp,
-                                                              dist, sel, hist, lists, ctl, out_ids, out_dist, fallback);
+                                                              g_single_prefetch, g_single_prefetch_rows, dist, sel, hist, lists, ctl, out_ids, out_dist, fallback);
     MORNA_LAUNCH_CHECK();
     return MORNA_OK;
 }

@@ -31,6 +31,7 @@ class MornaIndex(object):
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.sample_count = sample_count                 # morna.py:168
+        self.sample_count_is_exact = False               # True once count_samples produced it from this very input
         self.basename = basename
         self.internal_id_map = {}                        # :178
         self.new_internal_id = 0                         # :179
@@ -180,7 +181,7 @@ class MornaIndex(object):
             ws = _lib.workspace(lib.morna_assign_internal_ids_workspace_bytes(n_rows, nnz, max_sample_id), dev)
             _lib.check(lib.morna_assign_internal_ids(
                 _lib.dev_ptr(d_row_off), _lib.dev_ptr(d_pass), n_rows, _lib.dev_ptr(d_sample), nnz, max_sample_id,
-                _lib.dev_ptr(d_id_of), _lib.dev_ptr(d_n_kept), _lib.dev_ptr(ws), ws.numel(), sp),
+                int(self.sample_count) if self.sample_count_is_exact else 0, _lib.dev_ptr(d_id_of), _lib.dev_ptr(d_n_kept), _lib.dev_ptr(ws), ws.numel(), sp),
                 "morna_assign_internal_ids")
             n_kept = int(d_n_kept.item())
             if n_kept == 0:                              # morna.py:399-403
@@ -266,6 +267,7 @@ def go_index(intropolis, basename, features, n_trees, sample_count, sample_thres
                 out.flush()
     if seen is not None:
         index.sample_count = len(seen)
+        index.sample_count_is_exact = True               # distinct id strings >= distinct ids: the id pass may stop early
     if verbose:
         out.write("\nThere are %d samples.\n" % index.sample_count)
     if verbose:

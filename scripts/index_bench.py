@@ -11,7 +11,7 @@ from morna_b200 import _lib
 
 
 def run(pairs=500e6, samples=21504, dims=(500, 1000, 3000, 10000, 30000), threshold=100, cpu_pairs=5e6, splits=(), peak=None,
-        quiet=False):
+        quiet=False, tunings=()):
     """Returns {"pairs", "rows", "assign_internal_ids_ms", "per_features": {D: {...}}, "cpu_one_core_pairs_per_s"}."""
     def say(*a, **k):
         if not quiet:
@@ -76,7 +76,7 @@ def run(pairs=500e6, samples=21504, dims=(500, 1000, 3000, 10000, 30000), thresh
 
     d_id_of = torch.empty(N + 1, dtype=torch.int32, device=dev); d_n_kept = torch.zeros(1, dtype=torch.int32, device=dev)
     ws_ids = _lib.workspace(lib.morna_assign_internal_ids_workspace_bytes(J, nnz, N), dev)
-    t_ids = timed(lambda: _lib.check(lib.morna_assign_internal_ids(_lib.dev_ptr(d_row_off), _lib.dev_ptr(d_pass), J, _lib.dev_ptr(d_sample), nnz, N,
+    t_ids = timed(lambda: _lib.check(lib.morna_assign_internal_ids(_lib.dev_ptr(d_row_off), _lib.dev_ptr(d_pass), J, _lib.dev_ptr(d_sample), nnz, N, N,
                   _lib.dev_ptr(d_id_of), _lib.dev_ptr(d_n_kept), _lib.dev_ptr(ws_ids), ws_ids.numel(), sp), "ids"))
     n_kept = int(d_n_kept.item())
     nnz_pass = int(lens[passing == 1].sum())
@@ -91,6 +91,14 @@ def run(pairs=500e6, samples=21504, dims=(500, 1000, 3000, 10000, 30000), thresh
         acc_ld = (n_kept + 31) // 32 * 32
         d_acc = torch.empty(dim * acc_ld, dtype=torch.float64, device=dev)
         ws_acc = _lib.workspace(lib.morna_index_accumulate_workspace_bytes(J, nnz, dim), dev)
+        for tune in list(tunings):                      # "key=value": one timed accumulate per setting, defaults restored after
+            key, value = (int(x) for x in tune.split("="))
+            lib.morna_debug_set_tuning(key, value)
+            t_s = timed(lambda: _lib.check(lib.morna_index_accumulate(_lib.dev_ptr(d_row_off), _lib.dev_ptr(d_pass), _lib.dev_ptr(d_bucket), _lib.dev_ptr(d_sign),
+                        _lib.dev_ptr(d_idf), J, _lib.dev_ptr(d_sample), _lib.dev_ptr(d_cov), nnz, _lib.dev_ptr(d_id_of), N, 0, n_kept, dim, _lib.dev_ptr(d_acc),
+                        acc_ld, _lib.dev_ptr(ws_acc), ws_acc.numel(), sp), "acc"), reps=3)
+            say("D=%5d: tuning %s -> accumulate %.2f ms" % (dim, tune, t_s), flush=True)
+            lib.morna_debug_set_tuning(key, {12: 10, 25: 1, 8: 3}.get(key, 0))
         for split in list(splits):
             lib.morna_debug_set_tuning(12, split)
             t_s = timed(lambda: _lib.check(lib.morna_index_accumulate(_lib.dev_ptr(d_row_off), _lib.dev_ptr(d_pass), _lib.dev_ptr(d_bucket), _lib.dev_ptr(d_sign),
@@ -136,5 +144,7 @@ if __name__ == "__main__":
     ap.add_argument("--threshold", type=int, default=100)
     ap.add_argument("--cpu-pairs", type=float, default=5e6)
     ap.add_argument("--splits", type=str, default="", help="sweep morna_debug_set_tuning key 12 (log2 width of the sample-id ranges of the warp-per-range scatter-add)")
+    ap.add_argument("--tunings", type=str, default="", help="comma list of key=value for morna_debug_set_tuning, each timed on the accumulate call")
     a = ap.parse_args()
-    run(a.pairs, a.samples, [int(x) for x in a.dims.split(",")], a.threshold, a.cpu_pairs, [int(x) for x in a.splits.split(",") if x])
+    run(a.pairs, a.samples, [int(x) for x in a.dims.split(",")], a.threshold, a.cpu_pairs, [int(x) for x in a.splits.split(",") if x],
+        tunings=[x for x in a.tunings.split(",") if x])

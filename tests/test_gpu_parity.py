@@ -145,6 +145,43 @@ def test_index_build_rows_with_repeated_or_unsorted_samples():
     assert np.array_equal(idx.matrix_f32(), oracle.matrix_f32())
 
 
+@pytest.mark.parametrize("late_row", [10, 100, 2000])
+def test_id_pass_early_exit_keeps_the_first_seen_order(late_row):
+    """The id pass checks after 1/64 and 1/8 of the rows whether every sample id has been met and skips the rest if so.
+    One sample is held back until `late_row` (inside the first stretch, the second, or near the end); ids 0 and 7 never
+    pass the threshold at all in the last case's variant (an id space with holes never exits early)."""
+    from morna_b200 import _lib
+    from morna_b200.index import MornaIndex
+    lib = _lib.load()
+    rng = np.random.default_rng(late_row)
+    n_rows, n_samples = 2048, 300
+    rows = []
+    for j in range(n_rows):
+        pool = n_samples if j >= late_row else n_samples - 1
+        samples = rng.choice(pool, size=40, replace=False)
+        if j == late_row:
+            samples[0] = n_samples - 1
+        if j % 3:
+            samples = np.sort(samples)
+        rows.append(("chr1 %d %d" % (j, j + 9), samples.tolist(), rng.integers(1, 9, size=40).tolist()))
+    want, order = {}, 0
+    for _, samples, _ in rows:                              # morna.py:377-382
+        for sid in samples:
+            if sid not in want:
+                want[sid] = order
+                order += 1
+    maps = []
+    for early in (1, 0):
+        lib.morna_debug_set_tuning(25, early)
+        idx = MornaIndex(n_samples, "unused", dim=64, sample_threshold=1)
+        for row in rows:
+            idx.add_junction(*row)
+        idx.build()
+        maps.append(idx.internal_id_map)
+    lib.morna_debug_set_tuning(25, 1)
+    assert maps[0] == maps[1] == want
+
+
 def test_index_build_id_range_shards_concatenate():
     from morna_b200.index import MornaIndex
     rng = np.random.default_rng(21)
