@@ -178,25 +178,43 @@ struct RerankParams {
 // equal the exact scan's bit for bit.  Items are walked phase-major: with few rows and many queries
 // (rows re-ranked several times per batch) the row range of a phase stays L2-resident while all
 // queries pass over it; phases == 1 is the plain query-major gather.
-template <int kRows, bool kPipe = false>
-__global__ void __launch_bounds__(kRrThreads)
-rerank_dist_kernel(const RerankParams p) {
+constexpr int kRrFatSubs = 5;                  // groups of 4 warps in one SM-filling CTA (rerank_fat_kernel)
+
+template <int kRows, bool kPipe, int kSubs>
+__device__ __forceinline__ void rerank_dist_body(const RerankParams &p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *qs = reinterpret_cast<double *>(smem_raw);                   // [ld]  query * 2^896
+    // kSubs > 1: the CTA is kSubs independent groups of kRrThreads threads, each with its own staging area, its own
+    // named barrier and its own items (drawn from the batch's counter)
+    const int sub = kSubs > 1 ? (int)threadIdx.x / kRrThreads : 0;
+    const size_t sub_bytes = ((size_t)p.ld * sizeof(double) + (size_t)p.fcap * sizeof(int) + 15) & ~(size_t)15;
+    double *qs = reinterpret_cast<double *>(smem_raw + (size_t)sub * sub_bytes);      // [ld]  query * 2^896
     int *list = reinterpret_cast<int *>(qs + p.ld);                      // [fcap] positions in the candidate list
-    __shared__ int s_count;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int s_count_all[kSubs];
+    __shared__ long long s_item[kSubs];
+    int &s_count = s_count_all[sub];
+    auto group_sync = [&]() {
+        if (kSubs == 1) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" :: "r"(sub + 1), "n"(kRrThreads) : "memory");
+    };
+    const int tid = kSubs > 1 ? (int)threadIdx.x % kRrThreads : (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int chunks = (int)(p.ld >> 2);
     const uint64_t pol = l2_policy_evict_first();
     const int64_t total = (int64_t)p.nq * p.phases;
-    for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+    for (int64_t t = blockIdx.x; ; t += gridDim.x) {
+        if (kSubs > 1) {
+            group_sync();                                                // previous item is done with s_item
+            if (tid == 0) s_item[sub] = (long long)atomicAdd(p.queue, 1ULL);
+            group_sync();
+            t = s_item[sub];
+        }
+        if (t >= total) break;
         const int ph = (int)(t / p.nq), q = (int)(t - (int64_t)ph * p.nq);
         if (p.overflow[q]) continue;                                     // answered by the exact scan afterwards
         const int count = min(p.fin_cnt[q], p.fcap);
         const int32_t *ids = p.fin_id + (int64_t)q * p.fcap;
         const int lo = p.id_base + ph * p.phase_rows;
         const int hi = ph == p.phases - 1 ? INT_MAX : lo + p.phase_rows;
-        __syncthreads();                                                 // previous item is done with qs/list
+        group_sync();                                                 // previous item is done with qs/list
         if (warp == 0) {
             int m = 0;
             for (int i0 = 0; i0 < count; i0 += 32) {
@@ -209,7 +227,7 @@ rerank_dist_kernel(const RerankParams p) {
             }
             if (lane == 0) s_count = m;
         }
-        __syncthreads();
+        group_sync();
         const int m = s_count;
         if (m == 0) continue;
         {
@@ -224,7 +242,7 @@ rerank_dist_kernel(const RerankParams p) {
                 for (int c = tid; c < (int)p.ld; c += kRrThreads) qs[c] = c < p.dim ? qsrc[c] * kTwo896 : 0.0;
             }
         }
-        __syncthreads();
+        group_sync();
         const double qqv = p.qq[q];
         for (int g = warp * kRows; g < m; g += (kRrThreads / 32) * kRows) {
             const float4 *src[kRows];
@@ -241,6 +259,8 @@ rerank_dist_kernel(const RerankParams p) {
             for (int u = 0; u < kRows; ++u) acc[u] = 0.0;
             int c = lane;
             if (kPipe) {
+                // (Asking L2 for each row's lines 1-12 KB ahead of the loads with prefetch.global.L2, across pass boundaries,
+                // was measured: 0.78-0.93 ms against 0.79 -- the gather is bound by DRAM/L2 throughput, not by latency.)
                 // software pipeline: the loads of chunk step i+1 are in flight while step i is accumulated (the plain loop
                 // below waits for all its loads, then computes with nothing in flight: ncu shows 9 of 10 issue slots lost
                 // to long-scoreboard stalls)
@@ -327,6 +347,21 @@ rerank_dist_kernel(const RerankParams p) {
                 p.fin_dist[(int64_t)q * p.fcap + my_pos] = angular_from_sums(p.pp[my_row], qqv, mine);
         }
     }
+}
+
+template <int kRows, bool kPipe = false>
+__global__ void __launch_bounds__(kRrThreads)
+rerank_dist_kernel(const RerankParams p) {
+    rerank_dist_body<kRows, kPipe, 1>(p);
+}
+
+// The same work in CTAs that fill an SM each (kRrFatSubs groups of four warps, 140 KB of shared memory at D = 3000) and
+// come in clusters of two like the GEMM's CTA pairs: a launch of X such CTAs holds exactly X SMs and the scoring kernels of
+// the NEXT batch, launched with the remaining SMs as their grid, run beside it (SM partition).
+template <int kRows, bool kPipe>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kRrThreads * kRrFatSubs, 1)
+rerank_fat_kernel(const RerankParams p) {
+    rerank_dist_body<kRows, kPipe, kRrFatSubs>(p);
 }
 
 // ---- warp-granular re-rank: no shared-memory query, no block barriers -------------------------------------
@@ -1193,6 +1228,8 @@ static int g_rerank_ctas = 0;      // key 15: CTAs per SM of the warp kernel (0 
 static int g_rerank_subs = 0;      // key 16: items per query of the unsplit warp re-rank (0 = 4)
 static int g_side_job = 0;         // key 17: 1 = side jobs on: helper warps in the GEMM kernel re-rank the previous batch (measured slower:
                                    // the GEMM's TMA stream and the helpers' gathers queue behind each other)
+static int g_rerank_fat_sms = 0;   // key 30: > 0 = the re-rank runs as this many SM-filling CTAs ...
+static int g_gemm_pairs_cap = 0;   // key 31: ... and the GEMM kernels use at most this many CTA pairs (0 = all SMs)
 static int g_rerank_pipe = 1;      // key 18: CTA-per-query re-rank with software-pipelined row loads
 static long long *g_gemm_debug = nullptr;   // morna_debug_gemm_counters: device buffer for the MMA thread's wait counters
 static int g_gemm_relaxed_ns = 0;  // key 22
@@ -1240,6 +1277,7 @@ static int launch_knn_gemm(const CUtensorMap &tmap_q, const CUtensorMap &tmap_s,
     if (rca != MORNA_OK) return rca;
     int tiles = ((gp.m_blocks + 1) / 2) * gp.n_tiles;
     int pairs = sm_count_b() / 2;
+    if (g_gemm_pairs_cap > 0 && pairs > g_gemm_pairs_cap) pairs = g_gemm_pairs_cap;     // SM partition: the rest belongs to the re-rank
     if (tiles < pairs) pairs = tiles;
     RerankParams rr{};
     if (side) rr = *side;
@@ -1699,7 +1737,19 @@ extern "C" int morna_knn_batched_rerank(const float *vectors, const double *pp, 
         int64_t rr_grid = (int64_t)per_sm * sm_count_b();
         if (rr_grid > items || g_rerank_oneshot) rr_grid = items;
         if (g_carveout_hint) cudaFuncSetAttribute((const void *)kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        kern<<<(unsigned)rr_grid, kRrThreads, rr_smem, s>>>(rp);
+        const size_t fat_smem = (((size_t)ld * sizeof(double) + (size_t)kFinCap * sizeof(int) + 15) & ~(size_t)15) * kRrFatSubs;
+        if (g_rerank_fat_sms > 0 && rp.phases == 1 && fat_smem <= 200 * 1024) {
+            // SM partition: X SM-filling CTAs (in pairs); the scoring kernels' grids leave those SMs alone (key 30)
+            auto fat = rerank_fat_kernel<4, true>;
+            if ((rc = ensure_dynamic_smem((const void *)fat, fat_smem)) != MORNA_OK) return rc;
+            MORNA_CUDA_TRY(cudaMemsetAsync(rp.queue, 0, sizeof(unsigned long long), s));
+            int ctas = g_rerank_fat_sms / 2 * 2;
+            if (ctas > sm_count_b()) ctas = sm_count_b() / 2 * 2;
+            if (ctas < 2) ctas = 2;
+            fat<<<(unsigned)ctas, kRrThreads * kRrFatSubs, fat_smem, s>>>(rp);
+        } else {
+            kern<<<(unsigned)rr_grid, kRrThreads, rr_smem, s>>>(rp);
+        }
         MORNA_LAUNCH_CHECK();
     }
     const size_t or_smem = (size_t)kFinCap * (sizeof(double) + sizeof(int));
@@ -1786,6 +1836,8 @@ extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
     else if (key == 16) g_rerank_subs = value;
     else if (key == 17) g_side_job = value;
     else if (key == 18) g_rerank_pipe = value;
+    else if (key == 30) g_rerank_fat_sms = value > 0 ? value : 0;
+    else if (key == 31) g_gemm_pairs_cap = value > 0 ? value : 0;
     else if (key == 19) g_carveout_hint = value;
     else if (key == 20) g_rerank_oneshot = value;
     else if (key == 22) g_gemm_relaxed_ns = value;

@@ -177,6 +177,29 @@ def test_rerank_variants_agree(kernel, pipe, rows_per_warp, phase_mb):
             lib.morna_debug_set_tuning(key, val)
 
 
+@pytest.mark.parametrize("fat_sms,pairs", [(8, 4), (60, 44), (2, 0)])
+def test_sm_partition_changes_no_bit(fat_sms, pairs):
+    """The re-rank as SM-filling CTAs in pairs drawing queries from the batch's counter (key 30) beside scoring kernels held
+    to a number of CTA pairs (key 31) -- the SM-partition experiment -- returns the same lists, synchronously and streamed."""
+    from morna_b200 import _lib
+    lib = _lib.load()
+    try:
+        assert lib.morna_debug_set_tuning(30, fat_sms) == 0 and lib.morna_debug_set_tuning(31, pairs) == 0
+        rng = np.random.default_rng(77)
+        n, d, nq, k = 5000, 200, 700, 40
+        S = rng.standard_normal((n, d)).astype(np.float32)
+        srch = make_search(S)
+        batches = [S[rng.permutation(n)[:nq]].astype(np.float64) + 0.05 * rng.standard_normal((nq, d)) for _ in range(4)]
+        want = [srch.exact_search_device(torch.from_numpy(b).cuda(), k) for b in batches]
+        b_ids, b_d = srch.batched_search_device(torch.from_numpy(batches[0]).cuda(), k)
+        assert torch.equal(b_ids, want[0][0]) and torch.equal(b_d, want[0][1])
+        for (ids, dd), (w_ids, w_d) in zip(srch.search_batches(batches, k), want):
+            assert np.array_equal(ids, w_ids.cpu().numpy()) and np.array_equal(dd, w_d.cpu().numpy())
+    finally:
+        lib.morna_debug_set_tuning(30, 0)
+        lib.morna_debug_set_tuning(31, 0)
+
+
 @pytest.mark.parametrize("side", [1, 0])
 def test_side_job_pipeline_equals_the_synchronous_call(side):
     """The scoring call of batch i+1 carrying batch i's re-rank as its side job (helper warps inside the GEMM kernel,
