@@ -164,6 +164,7 @@ struct RerankParams {
     const double *queries; int64_t q_ld; const double *qq;
     const int32_t *fin_id; const int32_t *fin_cnt; const uint8_t *overflow;
     int32_t fcap, nq, phases, phase_rows;
+    int32_t rows_evict_first;       // key 32: L2 policy of the candidate-row loads (0 evict_normal = default, 1 evict_first, 2 evict_last, 3 mixed, 4 no hint)
     double *fin_dist;
     unsigned long long *queue;      // warp kernel: next item; zero when the batch's lists are complete
     int32_t subs;                   // warp kernel: a query's candidate list is dealt out in 32-entry windows to `subs` items
@@ -199,6 +200,19 @@ __device__ __forceinline__ void rerank_dist_body(const RerankParams &p) {
     const int tid = kSubs > 1 ? (int)threadIdx.x % kRrThreads : (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int chunks = (int)(p.ld >> 2);
     const uint64_t pol = l2_policy_evict_first();
+    uint64_t row_pol;
+    const int rp_mode = p.rows_evict_first;          // 0 evict_normal, 1 evict_first, 2 evict_last, 3 half evict_last / half evict_first, 4 no hint
+    if (rp_mode == 1) row_pol = pol;
+    else if (rp_mode == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(row_pol));
+    else if (rp_mode == 3) asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.5;" : "=l"(row_pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(row_pol));
+    auto row_ld = [&](const float4 *ptr) {
+        if (rp_mode == 4) return ldg_stream_f4(ptr);
+        float4 r;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(ptr), "l"(row_pol));
+        return r;
+    };
     const int64_t total = (int64_t)p.nq * p.phases;
     for (int64_t t = blockIdx.x; ; t += gridDim.x) {
         if (kSubs > 1) {
@@ -267,13 +281,13 @@ __device__ __forceinline__ void rerank_dist_body(const RerankParams &p) {
                 float4 va[kRows], vb[kRows];
                 if (c < chunks) {
 #pragma unroll
-                    for (int u = 0; u < kRows; ++u) va[u] = ldg_stream_f4(src[u] + c);
+                    for (int u = 0; u < kRows; ++u) va[u] = row_ld(src[u] + c);
                 }
                 for (; c < chunks; c += 64) {
                     const int c2 = c + 32, c3 = c + 64;
                     if (c2 < chunks) {
 #pragma unroll
-                        for (int u = 0; u < kRows; ++u) vb[u] = ldg_stream_f4(src[u] + c2);
+                        for (int u = 0; u < kRows; ++u) vb[u] = row_ld(src[u] + c2);
                     }
                     {
                         const double2 qa = *reinterpret_cast<const double2 *>(qs + 4 * c);
@@ -288,7 +302,7 @@ __device__ __forceinline__ void rerank_dist_body(const RerankParams &p) {
                     }
                     if (c3 < chunks) {
 #pragma unroll
-                        for (int u = 0; u < kRows; ++u) va[u] = ldg_stream_f4(src[u] + c3);
+                        for (int u = 0; u < kRows; ++u) va[u] = row_ld(src[u] + c3);
                     }
                     if (c2 < chunks) {
                         const double2 qa = *reinterpret_cast<const double2 *>(qs + 4 * c2);
@@ -309,7 +323,7 @@ __device__ __forceinline__ void rerank_dist_body(const RerankParams &p) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int u = 0; u < kRows; ++u) v[h][u] = ldg_stream_f4(src[u] + c + 32 * h);
+                    for (int u = 0; u < kRows; ++u) v[h][u] = row_ld(src[u] + c + 32 * h);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const double2 qa = *reinterpret_cast<const double2 *>(qs + 4 * (c + 32 * h));
@@ -328,7 +342,7 @@ __device__ __forceinline__ void rerank_dist_body(const RerankParams &p) {
                 const double2 qb = *reinterpret_cast<const double2 *>(qs + 4 * c + 2);
 #pragma unroll
                 for (int u = 0; u < kRows; ++u) {
-                    const float4 v = ldg_stream_f4(src[u] + c);
+                    const float4 v = row_ld(src[u] + c);
                     acc[u] = fma(f32_scaled_f64(v.x), qa.x, acc[u]);
                     acc[u] = fma(f32_scaled_f64(v.y), qa.y, acc[u]);
                     acc[u] = fma(f32_scaled_f64(v.z), qb.x, acc[u]);
@@ -571,6 +585,7 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct GemmParams {
     int32_t relaxed_ns;    // > 0: epilogue warps sleep this long between polls of the accumulator barrier (key 22)
+    int32_t l2_keep;       // key 33, experiment: operand tiles loaded with an evict_last L2 policy
     int32_t dry_epilogue;  // key 23, timing experiments only: the filter epilogue finds the survivors but does not append them
     long long *debug;      // optional [gridDim.x][4] cycle counters of the MMA thread (full-barrier wait, accumulator wait, total) and the epilogue
     int32_t nq, n_begin, n_end, kblocks, m_blocks, n_tiles, mode, cap, id_base;
@@ -806,6 +821,8 @@ knn_gemm2_body(const CUtensorMap &tmap_q, const CUtensorMap &tmap_s, const GemmP
     if (warp == 0) {
         if (lane == 0) {     // ===== TMA producer (every CTA); bytes are counted on its pair leader's barrier
             int stage = 0; uint32_t phase = 0;
+            uint64_t keep = 0;                               // experiment (key 33): operand tiles marked evict_last in L2
+            if (p.l2_keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
             for (int t = pair; t < total_tiles; t += pairs) {
                 const int m_pair = m_pair_of(t), n_tile = t / m_groups;
                 const int row_q = m_pair * 2 * BM + (int)rank * BM;
@@ -816,10 +833,13 @@ knn_gemm2_body(const CUtensorMap &tmap_q, const CUtensorMap &tmap_s, const GemmP
                     const uint32_t a_dst = base + stage * STAGE_BYTES, b_dst = a_dst + A_BYTES;
                     const uint32_t bar0 = mapa_rank(full_bar(stage), leader_rank);
                     if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
-                    tma_load_2d_pair(a_dst, &tmap_q, bar0, kb * BK, row_q);
+                    if (p.l2_keep) tma_load_2d_pair_hint(a_dst, &tmap_q, bar0, kb * BK, row_q, keep);
+                    else tma_load_2d_pair(a_dst, &tmap_q, bar0, kb * BK, row_q);
                     if (kQuad)       // my quarter of the sample tile, to me and to my counterpart in the other pair
                         tma_load_2d_pair_multicast(b_dst + pair_in_cluster * (B_BYTES / 2), &tmap_s, bar0, kb * BK, row_s,
                                                    (uint16_t)((1u << crank) | (1u << (crank ^ 2u))));
+                    else if (p.l2_keep)
+                        tma_load_2d_pair_hint(b_dst, &tmap_s, bar0, kb * BK, row_s, keep);
                     else
                         tma_load_2d_pair(b_dst, &tmap_s, bar0, kb * BK, row_s);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -1228,6 +1248,8 @@ static int g_rerank_ctas = 0;      // key 15: CTAs per SM of the warp kernel (0 
 static int g_rerank_subs = 0;      // key 16: items per query of the unsplit warp re-rank (0 = 4)
 static int g_side_job = 0;         // key 17: 1 = side jobs on: helper warps in the GEMM kernel re-rank the previous batch (measured slower:
                                    // the GEMM's TMA stream and the helpers' gathers queue behind each other)
+static int g_rerank_evict_first = 0;   // key 32 (measured, scripts/rerank_policy_sweep.py: an explicit evict_normal hint is 1-4 % faster than none)
+static int g_gemm_l2_keep = 0;         // key 33
 static int g_rerank_fat_sms = 0;   // key 30: > 0 = the re-rank runs as this many SM-filling CTAs ...
 static int g_gemm_pairs_cap = 0;   // key 31: ... and the GEMM kernels use at most this many CTA pairs (0 = all SMs)
 static int g_rerank_pipe = 1;      // key 18: CTA-per-query re-rank with software-pipelined row loads
@@ -1417,7 +1439,7 @@ static int score_impl(const void *hs, int64_t ld_h, const float *rho_max, int64_
                    g_gemm_pair == 2 && !side_ptr && (w.nq_pad / gemm::BM) % 4 == 0 ? gemm2::BN_HALF / 2 : g_gemm_pair ? gemm2::BN_HALF : gemm::BN);
     if (rc != MORNA_OK) return rc;
     GemmParams gp{};
-    gp.debug = g_gemm_debug; gp.relaxed_ns = g_gemm_relaxed_ns; gp.dry_epilogue = g_gemm_dry;
+    gp.debug = g_gemm_debug; gp.relaxed_ns = g_gemm_relaxed_ns; gp.dry_epilogue = g_gemm_dry; gp.l2_keep = g_gemm_l2_keep;
     gp.nq = (int32_t)nq; gp.kblocks = (int32_t)(ld_h / gemm::BK); gp.m_blocks = (int32_t)(w.nq_pad / gemm::BM);
     gp.cap = kCandCap; gp.id_base = id_base; gp.pilot = pilot; gp.pilot_ld = w.pilot_ld; gp.thr = thr;
     gp.cand_score = cand_score; gp.cand_id = cand_id; gp.cand_cnt = cand_cnt;
@@ -1669,6 +1691,7 @@ static int make_rerank_params(RerankParams &rp, bool &warp_kernel, const float *
     rp.fin_id = (const int32_t *)(ws + w.fin_id); rp.fin_cnt = (const int32_t *)(ws + w.fin_cnt); rp.overflow = overflow;
     rp.fcap = kFinCap; rp.nq = (int32_t)nq; rp.fin_dist = (double *)(ws + w.fin_dist);
     rp.queue = (unsigned long long *)(ws + w.queue);
+    rp.rows_evict_first = g_rerank_evict_first;
     // phases: only when a row is re-ranked several times per batch (otherwise every row is read at
     // most about once and splitting would only re-read the queries)
     rp.phases = 1; rp.phase_rows = (int32_t)n; rp.subs = 1;
@@ -1836,6 +1859,8 @@ extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
     else if (key == 16) g_rerank_subs = value;
     else if (key == 17) g_side_job = value;
     else if (key == 18) g_rerank_pipe = value;
+    else if (key == 32) g_rerank_evict_first = value >= 0 && value <= 4 ? value : 0;
+    else if (key == 33) g_gemm_l2_keep = value ? 1 : 0;
     else if (key == 30) g_rerank_fat_sms = value > 0 ? value : 0;
     else if (key == 31) g_gemm_pairs_cap = value > 0 ? value : 0;
     else if (key == 19) g_carveout_hint = value;

@@ -198,10 +198,12 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
     if (tid == 0) s_huge = 0;
     if (blockIdx.x == 0 && tid == 0) ctl->stamp[0] = global_ns();
     if (prefetch_bytes > 0) {
-        // The query staging and the qq sum below take ~3 us in which no row is read.  Pull this warp's first-pass rows
-        // into L2 meanwhile (no registers held): HBM starts streaming at once.  Measured (scripts/single_prefetch_sweep.py,
-        // 21,504 x 3000): 59.0 -> 55.5 us per query with whole first-pass rows (half the matrix = the L2's size); more
-        // rows, or prefetching every next pass from inside the loop, overflow L2 and cost 2-20 us.
+        // The query staging and the qq sum below take ~3 us in which no row is read.  Pull the head of this warp's
+        // first-pass rows into L2 meanwhile (no registers held): HBM starts streaming at once.  Measured at 21,504 x 3000
+        // (scripts/single_prefetch_sweep.py, scripts/single_bench_ab.py): 6 KB per row -- a quarter of the matrix -- gives
+        // 59.1 -> 55.8 us one query at a time and 39.2 -> 37.0 us with two in flight; whole rows (half the matrix = the
+        // L2's size) give 55.5 us but 42.5 us with two in flight, and more rows or prefetching from inside the loop
+        // overflow L2 (57-78 us).
         const int64_t gw0 = (int64_t)blockIdx.x * kS1Warps + warp;
         const int64_t first = gw0 * rows_per_warp;
         const int lines = min(prefetch_bytes, (int)(ld * 4)) >> 7;            // 128-byte lines per row
@@ -435,7 +437,7 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
     if (tid == 0) ctl->stamp[3] = global_ns();
 }
 
-static int g_single_prefetch = 1 << 20;   // morna_debug_set_tuning key 27: bytes (clamped to the row) of each first-pass row pulled into L2 before the query is staged
+static int g_single_prefetch = 6144;   // morna_debug_set_tuning key 27: bytes (clamped to the row) of each first-pass row pulled into L2 before the query is staged
 void set_single_prefetch(int v) { g_single_prefetch = v >= 0 ? v : 0; }
 static int g_single_prefetch_rows = 0;   // key 28: rows of the warp's share covered by that prefetch (0 = the first pass)
 void set_single_prefetch_rows(int v) { g_single_prefetch_rows = v >= 0 ? v : 0; }

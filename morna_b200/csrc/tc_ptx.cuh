@@ -93,6 +93,15 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_leader), "r"(c0), "r"(c1) : "memory");
 }
 
+// the same with an L2 cache policy (createpolicy) on the tile's lines
+__device__ __forceinline__ void tma_load_2d_pair_hint(uint32_t dst, const CUtensorMap *m, uint32_t bar_leader, int32_t c0, int32_t c1,
+                                                      uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_leader), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+
 // The pair flavour with multicast: the tile lands at the same shared-memory offset in every CTA of `cta_mask` (cluster
 // ranks), and each destination's bytes are counted on the barrier at bar's offset in the destination's pair, in the CTA
 // whose rank parity is that of the CTA `bar_leader` points to (the even, MMA-issuing CTA of each pair).

@@ -12,8 +12,10 @@ N, D, Q, K = 50000, 3000, 4096, 100
 S = synth.gauss(N, D, "cuda")
 q, rows = synth.queries(S, Q)
 configs = [tuple(int(x) for x in a.split(":")) for a in sys.argv[1:]] or [(0, 0), (44, 52), (60, 44), (52, 48), (36, 56), (0, 0)]
-for fat, pairs in configs:
+for cfg in configs:
+    fat, pairs, evict_first, keep = (list(cfg) + [0, 0])[:4]          # keys 32 / 33: L2 policies of the row gather / the operand tiles
     lib.morna_debug_set_tuning(30, fat); lib.morna_debug_set_tuning(31, pairs)
+    lib.morna_debug_set_tuning(32, evict_first); lib.morna_debug_set_tuning(33, keep)
     s = MornaSearch(vectors=S, stats=(N, N, D))
     s.enable_tensor_path()
     pick = torch.arange(0, Q, 61, device="cuda")
@@ -34,6 +36,7 @@ for fat, pairs in configs:
         time.sleep(0.3)
         ms.append(m)
     ok2 = torch.equal(torch.as_tensor(last[0])[pick.cpu()], ref_ids.cpu()) and torch.equal(torch.as_tensor(last[1])[pick.cpu()], ref_d.cpu())
-    print("re-rank on %3d SMs, GEMM on %2d pairs: %s sum %.3f | pipeline %s ok=%s/%s" % (
-        fat, pairs, ", ".join("%s %.3f" % (n_[:6], v) for n_, v in zip(PHASE_NAMES, acc)), sum(acc), " ".join("%.3f" % m for m in ms[1:]), ok, ok2), flush=True)
-lib.morna_debug_set_tuning(30, 0); lib.morna_debug_set_tuning(31, 0)
+    print("re-rank on %3d SMs, GEMM on %2d pairs, rows evict_first=%d, tiles evict_last=%d: %s sum %.3f | pipeline %s ok=%s/%s" % (
+        fat, pairs, evict_first, keep, ", ".join("%s %.3f" % (n_[:6], v) for n_, v in zip(PHASE_NAMES, acc)), sum(acc), " ".join("%.3f" % m for m in ms[1:]), ok, ok2), flush=True)
+for key in (30, 31, 32, 33):
+    lib.morna_debug_set_tuning(key, 0)

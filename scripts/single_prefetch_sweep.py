@@ -48,4 +48,4 @@ for v in values:
     st = sws[16:80].view(torch.int64).cpu().tolist()
     print("prefetch %12s: %s us per query back to back | stamps: scan %.1f, select %.1f, order %.1f us" % (
         v, " ".join("%.1f" % t for t in best[v]), (st[1] - st[0]) / 1e3, (st[2] - st[1]) / 1e3, (st[3] - st[2]) / 1e3), flush=True)
-apply(str(1 << 20))
+apply('6144')

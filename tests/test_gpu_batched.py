@@ -177,6 +177,26 @@ def test_rerank_variants_agree(kernel, pipe, rows_per_warp, phase_mb):
             lib.morna_debug_set_tuning(key, val)
 
 
+def test_l2_policy_knobs_change_no_bit():
+    """L2 eviction policies of the re-rank's row loads (key 32) and of the GEMM's operand tiles (key 33) are hints only."""
+    from morna_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    n, d, nq, k = 3000, 160, 300, 25
+    S = rng.standard_normal((n, d)).astype(np.float32)
+    srch = make_search(S)
+    q = torch.from_numpy(S[rng.permutation(n)[:nq]].astype(np.float64) + 0.03 * rng.standard_normal((nq, d))).cuda()
+    e_ids, e_d = srch.exact_search_device(q, k)
+    try:
+        for rows_policy, keep in ((0, 0), (1, 0), (2, 1), (3, 0), (4, 1)):
+            assert lib.morna_debug_set_tuning(32, rows_policy) == 0 and lib.morna_debug_set_tuning(33, keep) == 0
+            b_ids, b_d = srch.batched_search_device(q, k)
+            assert torch.equal(b_ids, e_ids) and torch.equal(b_d, e_d)
+    finally:
+        lib.morna_debug_set_tuning(32, 0)
+        lib.morna_debug_set_tuning(33, 0)
+
+
 @pytest.mark.parametrize("fat_sms,pairs", [(8, 4), (60, 44), (2, 0)])
 def test_sm_partition_changes_no_bit(fat_sms, pairs):
     """The re-rank as SM-filling CTAs in pairs drawing queries from the batch's counter (key 30) beside scoring kernels held
