@@ -209,6 +209,17 @@ int morna_knn_single_workspace_init(void *workspace, size_t workspace_bytes, voi
 int morna_knn_single(const float *vectors, const double *pp, int64_t n, int32_t dim, int64_t ld,
                      int32_t id_base, const double *query, int32_t k, int32_t *out_ids, double *out_dist,
                      int32_t *fallback, void *workspace, size_t workspace_bytes, void *stream);
+/* A stream of single queries (the per-query loop of exact_search_nn, morna.py:697-712, called once per query of a
+ * query file): n_queries kernels of morna_knn_single back to back on `stream`, query j = queries + j*query_stride,
+ * answers in out_ids/out_dist[j*k ..], fallback[j] per query.  The kernels after the first are launched with
+ * programmatic stream serialisation: query j+1's scan begins when every CTA of query j has finished its share of the
+ * scan -- or, by default, of its first pass over its rows -- so one CTA's selection tail and the launch gap run under the next scan.  Every query is still one full pass
+ * over the matrix.  The workspace is TWO morna_knn_single workspaces back to back (2 * morna_knn_single_workspace_bytes(n)),
+ * each initialised with morna_knn_single_workspace_init; the queries must be ready before the call is enqueued. */
+int morna_knn_single_stream(const float *vectors, const double *pp, int64_t n, int32_t dim, int64_t ld,
+                            int32_t id_base, const double *queries, int64_t query_stride, int32_t n_queries,
+                            int32_t k, int32_t *out_ids, double *out_dist, int32_t *fallback, void *workspace,
+                            size_t workspace_bytes, void *stream);
 
 /* exact_search_nn over a SPARSE index (rows with at most morna_sparse_max_nnz() non-zero buckets, e.g. an index built
  * from a handful of junctions such as the reference's tests/tiny_intropolis.tsv, where thousands of rows are parallel
@@ -327,7 +338,8 @@ int morna_debug_tensor_scores(const void *hs, int64_t ld_h, const float *rho_max
  *   11 batched: rows before the first refinement (0 = key 9's value)        12 index: log2 width of the sample-id ranges (10..12)
  *   13 re-rank (CTA-per-query kernel): cap on resident CTAs per SM          14 re-rank kernel: 0 = warp-granular queue items, 1 = CTA per query
  *   15 re-rank (warp kernel): CTAs per SM (0 = what fits)                   16 re-rank: items per query when not split into phases (0 = 4)
- *   17 side jobs: 0 = helper warps off (resume calls then re-rank everything) */
+ *   17 side jobs: 0 = helper warps off (resume calls then re-rank everything)
+ *   29 single-query stream: 0 = plain launches, 1 = next query starts after the scan, 2 = after the first row pass (default) */
 int morna_debug_set_tuning(int32_t key, int32_t value);
 /* Experiment hook: [dev] int64[grid * 4] that the pair GEMM's MMA-issuing thread fills with the cycles it spent waiting for
  * operand tiles (TMA) and for a free accumulator (epilogue), and its total; NULL switches it off (default). */

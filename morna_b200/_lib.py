@@ -69,6 +69,8 @@ _SIGNATURES = {
     "morna_knn_single_workspace_init": (ctypes.c_int, [_c_vp, _c_sz, _c_vp]),
     "morna_knn_single": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i32, _c_i64, _c_i32, _c_vp, _c_i32, _c_vp, _c_vp,
                                         _c_vp, _c_vp, _c_sz, _c_vp]),
+    "morna_knn_single_stream": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i32, _c_i64, _c_i32, _c_vp, _c_i64, _c_i32, _c_i32,
+                                               _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_vp]),
     "morna_tensor_operand_ld": (_c_i64, [_c_i32]),
     "morna_prepare_tensor_operand": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i32, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp]),
     "morna_knn_batched_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_i32, _c_i32]),

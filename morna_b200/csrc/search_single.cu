@@ -173,12 +173,22 @@ __device__ void select_candidates(const float *__restrict__ score, int64_t n, in
     __syncthreads();
 }
 
+// A chain of queries on one stream (morna_knn_single_stream): the kernels after the first are launched with
+// programmatic stream serialisation, so query j+1's kernel may begin once every CTA of query j's kernel has called
+// this -- after its share of the scan -- and its scan then runs under query j's selection tail (one CTA, ~7 us, 147 SMs
+// idle) and the launch gap.  Workspaces alternate between two halves: the wait BEFORE the trigger makes "kernel j+1
+// let kernel j+2 start" imply "kernel j has completed", so the half kernel j+2 reuses is free and zeroed again.
+__device__ __forceinline__ void chain_handoff() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // rows per warp pass R, chunk steps in flight U (R*U 16-byte loads per lane)
 template <int R, int U>
 __global__ void __launch_bounds__(kS1Threads, 2)
 scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict__ pp, int64_t n, int64_t ld,
                      int32_t dim, int32_t id_base, const double *__restrict__ query, int32_t k, int64_t rows_per_warp,
-                     int32_t prefetch_bytes, int32_t prefetch_rows, double *__restrict__ dist, float *__restrict__ sel, unsigned int *__restrict__ hist,
+                     int32_t prefetch_bytes, int32_t prefetch_rows, int32_t chain, double *__restrict__ dist, float *__restrict__ sel, unsigned int *__restrict__ hist,
                      int32_t *__restrict__ lists, SingleWs *ctl,
                      int32_t *__restrict__ out_ids, double *__restrict__ out_dist, int32_t *__restrict__ fallback_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -227,6 +237,7 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
     __syncthreads();
     if (s_huge) {                        // q * 2^896 is not finite: the generic FP64 scan answers
         if (blockIdx.x == 0 && tid == 0) *fallback_out = 1;
+        if (chain) chain_handoff();      // (a kernel of a chain never ends before its predecessor: the kernel after it reuses that one's workspace)
         return;
     }
     // qq with the canonical tree (every warp computes it for itself; 2^-896 undoes the staging exactly)
@@ -295,6 +306,7 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
             const unsigned int slot = atomicAdd(hist + bin, 1u);
             if (slot < kBinCap) lists[bin * kBinCap + slot] = (int)(r + lane);
         }
+        if (chain == 2 && r == row_begin) chain_handoff();
     }
     for (; r < row_end; ++r) {                                         // leftover rows of this warp, one at a time
         const float4 *src = reinterpret_cast<const float4 *>(vectors + r * ld);
@@ -316,6 +328,7 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
             if (slot < kBinCap) lists[bin * kBinCap + slot] = (int)r;
         }
     }
+    if (chain == 1 || (chain == 2 && row_end - row_begin <= R)) chain_handoff();
     // last CTA to arrive answers the query from all keys
     __threadfence();
     __syncthreads();
@@ -463,10 +476,22 @@ static SingleLayout single_layout(int64_t n) {
 template <int R, int U>
 static int launch_scan64(unsigned grid, size_t smem, cudaStream_t s, const float *vectors, const double *pp, int64_t n,
                          int64_t ld, int32_t dim, int32_t id_base, const double *query, int32_t k, int64_t rows_per_warp,
-                         double *dist, float *sel, unsigned int *hist, int32_t *lists, SingleWs *ctl, int32_t *out_ids, double *out_dist, int32_t *fallback) {
+                         double *dist, float *sel, unsigned int *hist, int32_t *lists, SingleWs *ctl, int32_t *out_ids, double *out_dist, int32_t *fallback,
+                         int chain, bool early) {
     { int rca = ensure_dynamic_smem((const void *)scan64_select_kernel<R, U>, smem); if (rca != MORNA_OK) return rca; }
-    scan64_select_kernel<R, U><<<grid, kS1Threads, smem, s>>>(vectors, pp, n, ld, dim, id_base, query, k, rows_per_warp,
-                                                              g_single_prefetch, g_single_prefetch_rows, dist, sel, hist, lists, ctl, out_ids, out_dist, fallback);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kS1Threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = early ? 1 : 0;          // early: may begin before the preceding kernel of the chain has drained
+    MORNA_CUDA_TRY(cudaLaunchKernelEx(&cfg, scan64_select_kernel<R, U>, vectors, pp, n, ld, dim, id_base, query, k, rows_per_warp,
+                                      (int32_t)g_single_prefetch, (int32_t)g_single_prefetch_rows, (int32_t)chain, dist, sel, hist, lists,
+                                      ctl, out_ids, out_dist, fallback));
     MORNA_LAUNCH_CHECK();
     return MORNA_OK;
 }
@@ -485,9 +510,9 @@ extern "C" int morna_knn_single_workspace_init(void *workspace, size_t workspace
     return MORNA_OK;
 }
 
-extern "C" int morna_knn_single(const float *vectors, const double *pp, int64_t n, int32_t dim, int64_t ld,
-                                int32_t id_base, const double *query, int32_t k, int32_t *out_ids, double *out_dist,
-                                int32_t *fallback, void *workspace, size_t workspace_bytes, void *stream) {
+static int knn_single_launch(const float *vectors, const double *pp, int64_t n, int32_t dim, int64_t ld,
+                             int32_t id_base, const double *query, int32_t k, int32_t *out_ids, double *out_dist,
+                             int32_t *fallback, void *workspace, size_t workspace_bytes, void *stream, int chain, bool early) {
     if (!vectors || !pp || !query || !out_ids || !out_dist || !fallback || n <= 0 || n > 0x7fffffff || dim <= 0 ||
         ld < dim || (ld & 3) || k <= 0 || k > kS1Cand / 2)
         return MORNA_ERR_INVALID_ARGUMENT;
@@ -524,10 +549,40 @@ extern "C" int morna_knn_single(const float *vectors, const double *pp, int64_t 
     const unsigned grid = (unsigned)((warps + kS1Warps - 1) / kS1Warps);
 #define MORNA_SCAN64(RR, UU)                                                                                          \
     case RR: return launch_scan64<RR, UU>(grid, smem, s, vectors, pp, n, ld, dim, id_base, query, k, rpw, dist, sel, \
-                                          hist, lists, ctl, out_ids, out_dist, fallback)
+                                          hist, lists, ctl, out_ids, out_dist, fallback, chain, early)
     switch (R) {
         MORNA_SCAN64(1, 8); MORNA_SCAN64(2, 4); MORNA_SCAN64(3, 2); MORNA_SCAN64(4, 2); MORNA_SCAN64(5, 1);
     }
 #undef MORNA_SCAN64
     return MORNA_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int morna_knn_single(const float *vectors, const double *pp, int64_t n, int32_t dim, int64_t ld,
+                                int32_t id_base, const double *query, int32_t k, int32_t *out_ids, double *out_dist,
+                                int32_t *fallback, void *workspace, size_t workspace_bytes, void *stream) {
+    return knn_single_launch(vectors, pp, n, dim, ld, id_base, query, k, out_ids, out_dist, fallback, workspace, workspace_bytes,
+                             stream, 0, false);
+}
+
+static int g_single_chain = 2;      // morna_debug_set_tuning key 29: 0 = plain launches, 1 = hand over after the scan, 2 = after the first pass (measured
+                                    // at 21,504 x 3000, scripts/single_chain_probe.py: 58.3 / 49.0 / 44.5 us per query)
+namespace morna { void set_single_chain(int v) { g_single_chain = v < 0 ? 0 : (v > 2 ? 2 : v); } }
+
+extern "C" int morna_knn_single_stream(const float *vectors, const double *pp, int64_t n, int32_t dim, int64_t ld,
+                                       int32_t id_base, const double *queries, int64_t query_stride, int32_t n_queries,
+                                       int32_t k, int32_t *out_ids, double *out_dist, int32_t *fallback, void *workspace,
+                                       size_t workspace_bytes, void *stream) {
+    if (n_queries < 0 || (n_queries > 0 && (!queries || query_stride < dim))) return MORNA_ERR_INVALID_ARGUMENT;
+    const size_t half = single_layout(n > 0 ? n : 1).total;
+    if (!workspace || workspace_bytes < 2 * half) return MORNA_ERR_WORKSPACE_TOO_SMALL;
+    const int chain = g_single_chain;
+    for (int32_t j = 0; j < n_queries; ++j) {
+        // the first kernel is an ordinary launch: it starts after everything the stream already holds, inputs included
+        const int rc = knn_single_launch(vectors, pp, n, dim, ld, id_base, queries + (int64_t)j * query_stride, k,
+                                         out_ids + (int64_t)j * k, out_dist + (int64_t)j * k, fallback + j,
+                                         (unsigned char *)workspace + (size_t)(j & 1) * half, half, stream, chain,
+                                         chain != 0 && j > 0);
+        if (rc != MORNA_OK) return rc;
+    }
+    return MORNA_OK;
 }

@@ -233,6 +233,51 @@ class MornaSearch(object):
                 return self.exact_search_device(query.view(1, -1), k, allow_single=False)
         return out_ids, out_d
 
+    def single_search_stream(self, queries, k):
+        """A stream of single queries (CUDA float64 [m x dim]), each answered by its own full pass of the
+        single-query kernel, launched back to back so that query j+1's scan runs under query j's selection tail
+        (morna_knn_single_stream; programmatic dependent launch, two alternating workspaces).  Same results as
+        single_search_device per query; queries whose ties overflow the lists are answered by the FP64 scan."""
+        assert queries.is_cuda and queries.dtype == torch.float64 and queries.dim() == 2 and queries.shape[1] == self.dim
+        queries = queries.contiguous()
+        m, n, dev = queries.shape[0], self.row_hi - self.row_lo, self.device
+        k_eff = min(int(k), n)
+        if m == 0 or n == 0 or k_eff <= 0 or k_eff > 512 or self.csr is not None:
+            return self.exact_search_device(queries, k, allow_single=False)
+        out_ids = torch.full((m, k), -1, dtype=torch.int32, device=dev)
+        out_d = torch.full((m, k), float("inf"), dtype=torch.float64, device=dev)
+        ids_k = out_ids if k_eff == k else torch.empty((m, k_eff), dtype=torch.int32, device=dev)
+        d_k = out_d if k_eff == k else torch.empty((m, k_eff), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            ws = self._single_stream_workspace(n)
+            flags = torch.zeros(m, dtype=torch.int32, device=dev)
+            _lib.check(self.lib.morna_knn_single_stream(
+                _lib.dev_ptr(self.vectors), _lib.dev_ptr(self.pp), n, self.dim, self.ld, self.row_lo,
+                _lib.ptr(queries), self.dim, m, k_eff, _lib.dev_ptr(ids_k), _lib.dev_ptr(d_k), _lib.dev_ptr(flags),
+                _lib.dev_ptr(ws), ws.numel(), _lib.stream_ptr()), "morna_knn_single_stream")
+            if k_eff != k:
+                out_ids[:, :k_eff] = ids_k
+                out_d[:, :k_eff] = d_k
+            redo = torch.nonzero(flags).flatten()
+            if redo.numel():
+                e_ids, e_d = self.exact_search_device(queries[redo], k, allow_single=False)
+                out_ids[redo] = e_ids
+                out_d[redo] = e_d
+        return out_ids, out_d
+
+    def _single_stream_workspace(self, n):
+        """Two single-query workspaces back to back (the halves alternate between consecutive queries), per stream."""
+        half = self.lib.morna_knn_single_workspace_bytes(n)
+        pool = self.__dict__.setdefault("_ws_pool", {})
+        key = ("single_stream", torch.cuda.current_stream(self.device).cuda_stream)
+        ws = pool.get(key)
+        if ws is None or ws.numel() < 2 * half:
+            ws = pool[key] = _lib.workspace(2 * half, self.device)
+            for h in (0, 1):
+                _lib.check(self.lib.morna_knn_single_workspace_init(ctypes.c_void_p(ws.data_ptr() + h * half), half, _lib.stream_ptr()),
+                           "morna_knn_single_workspace_init")
+        return ws
+
     MAX_SELECT_K = 2048              # kSelMaxK of morna_select_topk
     sparse_exact = False             # set at load for a sparse index whose tie groups would overflow the tensor path's lists
     TIE_GROUP_FOR_SPARSE_PATH = 512  # (the final candidate lists hold 1024 rows; a query usually sees two or more such groups)

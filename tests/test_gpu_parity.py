@@ -438,6 +438,40 @@ def _run_single_query_checks(n, d, k):
     check_topk(true_d, s_ids[0].cpu().numpy()[:m], s_d[0].cpu().numpy()[:m], tol=1e-9)
 
 
+@pytest.mark.parametrize("chain", [0, 1, 2])
+def test_single_query_stream_equals_one_query_at_a_time(chain):
+    """morna_knn_single_stream (back-to-back kernels, programmatic dependent launch, alternating workspaces) returns for
+    every query what morna_knn_single returns, which is pinned to the oracle above -- including queries that fall
+    back (huge values), many queries in one call (each workspace half reused many times) and repeated calls."""
+    from morna_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(17 + chain)
+    n, d, k = 9001, 300, 50
+    S = rng.standard_normal((n, d)).astype(np.float32) * np.exp(rng.standard_normal((n, 1))).astype(np.float32)
+    srch = make_search(S)
+    Q = np.concatenate([S[:20].astype(np.float64), rng.standard_normal((21, d))])
+    Q[7, 3] = 2e38                                     # answered by the generic scan
+    Qd = torch.from_numpy(Q).cuda()
+    try:
+        assert lib.morna_debug_set_tuning(29, chain) == 0
+        for _ in range(3):
+            ids, dist = srch.single_search_stream(Qd, k)
+    finally:
+        lib.morna_debug_set_tuning(29, 2)
+    for j in range(Q.shape[0]):
+        s_ids, s_d = srch.single_search_device(Qd[j], k)
+        assert torch.equal(ids[j], s_ids[0]) and torch.equal(dist[j], s_d[0]), "query %d" % j
+    true_d = c_oracle.distances(S, Q[30])
+    check_topk(true_d, ids[30].cpu().numpy(), dist[30].cpu().numpy(), tol=1e-9)
+    # k above the row count and an empty batch behave like the other entry points
+    small = make_search(S[:30])
+    i2, d2 = small.single_search_stream(Qd[:3], 40)
+    e2, f2 = small.exact_search_device(Qd[:3], 40, allow_single=False)
+    assert torch.equal(i2, e2) and torch.equal(d2, f2)
+    i3, _ = srch.single_search_stream(Qd[:0], k)
+    assert i3.shape == (0, k)
+
+
 def test_single_query_ties_fall_back_and_shard_offsets():
     oracle = mo.go_index(tiny_lines(), features=3000, sample_threshold=100)
     S = oracle.matrix_f32()
