@@ -502,144 +502,120 @@ def rows_sharded_line(torch, td, synth, MornaSearch, device, rank, world, n_rows
 
 
 def single_query_line(torch, lib, _lib, synth, device, peaks):
-    """BASELINE configs[1]: one exact top-100 query over 21,504 x 3000 rows (the single-query kernel, HBM-bound:
-    4*N*D algorithmic bytes per query), replayed back to back from a CUDA graph, CUDA events on the stream."""
+    """BASELINE configs[1]: exact top-100 single queries over 21,504 x 3000 rows (the single-query kernel, HBM-bound:
+    4*N*D algorithmic bytes per query).  Every figure is device time (CUDA events on the launching stream) of CUDA-graph
+    replays holding 32 kernels each, so the host's launch rate does not enter."""
     from morna_b200.search import MornaSearch
-    n = 21504
+    n, m = 21504, 32
     S = synth.gauss(n, DIM, device, 4321)
     srch = MornaSearch(vectors=S, stats=(n, n, DIM), device=device)
-    q = S[n // 3].to(torch.float64).contiguous()
-    side = torch.cuda.Stream(device=device)
-    with torch.cuda.stream(side):
-        ids, d = srch.single_search_device(q, K)
-        assert int(ids[0, 0]) == n // 3 and float(d[0, 0]) == 0.0 and int(srch._sfallback.item()) == 0
-        out_i = torch.empty((1, K), dtype=torch.int32, device=device)
-        out_d = torch.empty((1, K), dtype=torch.float64, device=device)
+    QS = S[torch.arange(m, device=device) * 600 + 7].to(torch.float64).contiguous()      # 32 distinct in-index queries
+    side, other = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    algo = 4.0 * n * DIM
 
-        def call():
-            _lib.check(lib.morna_knn_single(_lib.dev_ptr(srch.vectors), _lib.dev_ptr(srch.pp), n, DIM, srch.ld, 0, _lib.dev_ptr(q), K,
-                                            _lib.dev_ptr(out_i), _lib.dev_ptr(out_d), _lib.dev_ptr(srch._sfallback),
-                                            _lib.dev_ptr(srch._sws), srch._sws.numel(), _lib.stream_ptr()), "morna_knn_single")
-        for _ in range(3):
-            call()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
-            call()
-        for _ in range(5):
-            graph.replay()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 200
-        e0.record(side)
-        for _ in range(reps):
-            graph.replay()
-        e1.record(side)
-    side.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / reps
-    assert torch.equal(out_i, ids) and torch.equal(out_d, d)
-    # throughput with two queries in flight: a second stream with its own workspace and outputs; the last CTA's selection
-    # and the launch gap of one query then run under the next query's scan (per-query latency is unchanged)
-    other = torch.cuda.Stream(device=device)
-    with torch.cuda.stream(other):
-        ids2, d2 = srch.single_search_device(q, K)                 # creates this stream's workspace
-        sws2, flag2 = srch._sws, srch._sfallback
-        out_i2 = torch.empty((1, K), dtype=torch.int32, device=device)
-        out_d2 = torch.empty((1, K), dtype=torch.float64, device=device)
+    def entry(us):
+        return {"us_per_query": us, "queries_per_s": 1e6 / us, "achieved": algo / (us * 1e-6) / 1e9,
+                "frac": algo / (us * 1e-6) / 1e9 / peaks["hbm_gbs"]}
 
-        def call2():
-            _lib.check(lib.morna_knn_single(_lib.dev_ptr(srch.vectors), _lib.dev_ptr(srch.pp), n, DIM, srch.ld, 0, _lib.dev_ptr(q), K,
-                                            _lib.dev_ptr(out_i2), _lib.dev_ptr(out_d2), _lib.dev_ptr(flag2),
-                                            _lib.dev_ptr(sws2), sws2.numel(), _lib.stream_ptr()), "morna_knn_single")
-        for _ in range(3):
-            call2()
-        graph2 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph2, stream=other):
-            call2()
-    other.synchronize()
-    f0, f1, f2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    torch.cuda.synchronize(device)
-    f0.record(side)
-    other.wait_event(f0)
-    for _ in range(reps // 2):
+    class Arm:
+        """One stream's buffers and its captured graph of one morna_knn_single_stream call over `queries`."""
+        def __init__(self, stream, queries):
+            self.stream, self.q = stream, queries
+            with torch.cuda.stream(stream):
+                self.want_i, self.want_d = srch.single_search_stream(queries, K)
+                self.ws = srch._single_stream_workspace(n)
+                self.flags = torch.zeros(queries.shape[0], dtype=torch.int32, device=device)
+                self.ids, self.d = torch.empty_like(self.want_i), torch.empty_like(self.want_d)
+            stream.synchronize()
+
+        def call(self):
+            q = self.q
+            _lib.check(lib.morna_knn_single_stream(_lib.dev_ptr(srch.vectors), _lib.dev_ptr(srch.pp), n, DIM, srch.ld, 0, _lib.dev_ptr(q), DIM,
+                                                   q.shape[0], K, _lib.dev_ptr(self.ids), _lib.dev_ptr(self.d), _lib.dev_ptr(self.flags),
+                                                   _lib.dev_ptr(self.ws), self.ws.numel(), _lib.stream_ptr()), "morna_knn_single_stream")
+
+        def capture(self):
+            with torch.cuda.stream(self.stream):
+                for _ in range(2):
+                    self.call()
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, stream=self.stream):
+                    self.call()
+                for _ in range(3):
+                    self.graph.replay()
+            self.stream.synchronize()
+
+        def check(self):
+            assert torch.equal(self.ids, self.want_i) and torch.equal(self.d, self.want_d) and int(self.flags.sum()) == 0
+
+    main_arm = Arm(side, QS)
+    for j in (0, 13, 31):                                          # the stream call answers like the one-query call
+        one_i, one_d = srch.single_search_device(QS[j], K)
+        assert torch.equal(main_arm.want_i[j], one_i[0]) and torch.equal(main_arm.want_d[j], one_d[0])
+        assert int(one_i[0, 0]) == j * 600 + 7 and float(one_d[0, 0]) == 0.0
+    # hand-over 0: plain launches, every kernel starts after the previous one has drained (one query at a time);
+    # 1: programmatic dependent launch, the next kernel begins when every CTA of the current one has finished its scan --
+    #    consecutive scans do not overlap, only the one-CTA selection tail and the launch gap are hidden;
+    # 2 (library default): ... has finished its first row pass -- consecutive scans overlap by about half
+    res = {}
+    for mode, name in ((0, "plain_launches"), (1, "handover_after_scan"), (2, "handover_after_first_pass")):
+        lib.morna_debug_set_tuning(29, mode)
+        main_arm.capture()
         with torch.cuda.stream(side):
-            graph.replay()
-        with torch.cuda.stream(other):
-            graph2.replay()
-    f1.record(side); f2.record(other)
-    torch.cuda.synchronize(device)
-    us2 = max(f0.elapsed_time(f1), f0.elapsed_time(f2)) * 1e3 / (2 * (reps // 2))
-    assert torch.equal(out_i2, ids) and torch.equal(out_d2, d) and torch.equal(out_i, ids)
-    # a stream of single queries on ONE CUDA stream (morna_knn_single_stream): 32 distinct queries per call, every query its
-    # own kernel and its own full pass over the matrix; programmatic dependent launch lets the next kernel begin when every
-    # CTA of the current one has finished its scan (hand-over 1: only the one-CTA selection tail and the launch gap are hidden)
-    # or its first row pass (hand-over 2, the library default: consecutive scans overlap by about half)
-    m = 32
-    QS = S[torch.arange(m, device=device) * 600 + 7].to(torch.float64).contiguous()
-    chained = {}
-    with torch.cuda.stream(side):
-        want_i, want_d = srch.single_search_stream(QS, K)
-        for j in (0, 13, 31):
-            one_i, one_d = srch.single_search_device(QS[j], K)
-            assert torch.equal(want_i[j], one_i[0]) and torch.equal(want_d[j], one_d[0])
-        ws2h = srch._single_stream_workspace(n)
-        flags = torch.zeros(m, dtype=torch.int32, device=device)
-        s_i, s_d = torch.empty_like(want_i), torch.empty_like(want_d)
-
-        def stream_call():
-            _lib.check(lib.morna_knn_single_stream(_lib.dev_ptr(srch.vectors), _lib.dev_ptr(srch.pp), n, DIM, srch.ld, 0, _lib.dev_ptr(QS), DIM, m, K,
-                                                   _lib.dev_ptr(s_i), _lib.dev_ptr(s_d), _lib.dev_ptr(flags), _lib.dev_ptr(ws2h), ws2h.numel(),
-                                                   _lib.stream_ptr()), "morna_knn_single_stream")
-        for mode, name in ((1, "handover_after_scan"), (2, "handover_after_first_pass")):
-            lib.morna_debug_set_tuning(29, mode)
-            for _ in range(2):
-                stream_call()
-            g3 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g3, stream=side):
-                stream_call()
-            for _ in range(3):
-                g3.replay()
             e0.record(side)
             for _ in range(10):
-                g3.replay()
+                main_arm.graph.replay()
             e1.record(side)
-            side.synchronize()
-            us_c = e0.elapsed_time(e1) * 1e3 / (10 * m)
-            assert torch.equal(s_i, want_i) and torch.equal(s_d, want_d) and int(flags.sum()) == 0
-            chained[name] = {"us_per_query": us_c, "queries_per_s": 1e6 / us_c, "achieved": 4.0 * n * DIM / (us_c * 1e-6) / 1e9,
-                             "frac": 4.0 * n * DIM / (us_c * 1e-6) / 1e9 / peaks["hbm_gbs"]}
-        lib.morna_debug_set_tuning(29, 2)
+        side.synchronize()
+        main_arm.check()
+        res[name] = entry(e0.elapsed_time(e1) * 1e3 / (10 * m))
+    # two CUDA streams, each with its own workspaces, plain launches: two queries in flight
+    lib.morna_debug_set_tuning(29, 0)
+    arm_a, arm_b = Arm(side, QS[:m // 2].contiguous()), Arm(other, QS[m // 2:].contiguous())
+    arm_a.capture(); arm_b.capture()
+    torch.cuda.synchronize(device)
+    e0.record(side)
+    other.wait_event(e0)
+    for _ in range(10):
+        with torch.cuda.stream(side):
+            arm_a.graph.replay()
+        with torch.cuda.stream(other):
+            arm_b.graph.replay()
+    e1.record(side); e2.record(other)
+    torch.cuda.synchronize(device)
+    arm_a.check(); arm_b.check()
+    two = entry(max(e0.elapsed_time(e1), e0.elapsed_time(e2)) * 1e3 / (10 * m))
+    two["what"] = "plain launches on two CUDA streams, each with its own workspaces: two independent queries in flight"
+    lib.morna_debug_set_tuning(29, 2)
     # end to end: host query in (pinned), host ids + distances out, one query at a time through the public call
-    hq = q.cpu().pin_memory()
+    hq = QS[5].cpu().pin_memory()
     for _ in range(5):
         srch.exact_search_batch(hq.numpy()[None, :], K)
     t0 = time.perf_counter()
     for _ in range(50):
         hi_, hd_ = srch.exact_search_batch(hq.numpy()[None, :], K)
     e2e_us = (time.perf_counter() - t0) / 50 * 1e6
-    assert int(hi_[0, 0]) == n // 3
-    gbs = 4.0 * n * DIM / (us * 1e-6) / 1e9
-    gbs2 = 4.0 * n * DIM / (us2 * 1e-6) / 1e9
-    us_s = chained["handover_after_scan"]["us_per_query"]
-    gbs_s = 4.0 * n * DIM / (us_s * 1e-6) / 1e9
+    assert int(hi_[0, 0]) == 5 * 600 + 7
     traffic = None
     prof = os.path.join(ROOT, "profiles", "r01_step_summary.json")     # dram bytes per launch from the committed ncu capture
     if os.path.exists(prof):
         with open(prof) as fh:
             traffic = json.load(fh).get("scan64_dram_bytes_21504x3000")
-    return {"workload": "21504 samples x 3000 features, one query, exact top-100 (the 258 MB matrix exceeds L2)",
-            "us_per_query": us_s, "queries_per_s": 1e6 / us_s, "kernel": "scan64_select_kernel (one launch per query)",
+    head = res["handover_after_scan"]
+    return {"workload": "21504 samples x 3000 features, single queries, exact top-100 (the 258 MB matrix exceeds L2)",
+            "us_per_query": head["us_per_query"], "queries_per_s": head["queries_per_s"],
+            "kernel": "scan64_select_kernel (one launch per query)",
             "what": "a stream of single queries on one CUDA stream (morna_knn_single_stream, 32 distinct queries per call, CUDA-graph replay), "
                     "every query its own kernel and its own full pass over the matrix; query j+1's kernel is launched with programmatic stream "
                     "serialisation and begins when every CTA of query j has finished its scan, so consecutive scans do not overlap: only the "
-                    "one-CTA selection tail and the launch gap are hidden",
-            "isolated": {"us_per_query": us, "queries_per_s": 1e6 / us, "achieved": gbs, "frac": gbs / peaks["hbm_gbs"],
-                         "what": "morna_knn_single replayed one at a time (each kernel starts after the previous one has drained)"},
-            "stream": chained,
-            "two_in_flight": {"us_per_query": us2, "queries_per_s": 1e6 / us2, "achieved": gbs2, "frac": gbs2 / peaks["hbm_gbs"],
-                              "what": "the same call replayed alternately on two streams, each with its own workspace: throughput of a stream of "
-                                      "single queries (one query's selection tail and launch gap hide under the next query's scan)"},
+                    "one-CTA selection tail and the launch gap are hidden (`stream.handover_after_scan`).  `stream.plain_launches` is one query "
+                    "at a time with nothing hidden; `stream.handover_after_first_pass` is the library default (consecutive scans overlap)",
+            "stream": res, "two_in_flight": two,
             "e2e": {"us_per_query": e2e_us, "queries_per_s": 1e6 / e2e_us, "h2d_bytes": DIM * 8, "d2h_bytes": K * 12,
                     "what": "MornaSearch.exact_search_batch with one host query: pinned copy in, kernel, ids + distances copied out, synchronous"},
-            "roofline": {"bound": "hbm", "achieved": gbs_s, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs_s / peaks["hbm_gbs"],
+            "roofline": {"bound": "hbm", "achieved": head["achieved"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": head["frac"],
+                         "frac_plain_launches": res["plain_launches"]["frac"], "frac_overlapping_scans": res["handover_after_first_pass"]["frac"],
                          "traffic": traffic, "traffic_source": "static: dram__bytes_read+write of one launch in the committed ncu capture (profiles/), not measured in this run",
                          "algorithmic": "4*N*D bytes per query"}}
 
