@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MORNA_ABI_VERSION 3
+#define MORNA_ABI_VERSION 4
 
 enum {
     MORNA_OK = 0,

@@ -21,7 +21,7 @@ ERR_NO_SAMPLES = -5
 ERR_CAPACITY = -6
 
 _c_i32, _c_i64, _c_sz, _c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t, ctypes.c_void_p
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class RerankJob(ctypes.Structure):

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name + " declared in include/morna_b200.h but not exported"
     assert set(declared) == set(_lib.EXPORTED_SYMBOLS), "ctypes table and header disagree"
-    assert _lib.load().morna_abi_version() == _lib.ABI_VERSION == 3
+    assert _lib.load().morna_abi_version() == _lib.ABI_VERSION == 4
     assert _lib.load().morna_status_string(-2) == b"workspace too small"
 
 
