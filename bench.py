@@ -334,6 +334,14 @@ def main():
         extras["rows_sharded"] = rows_sharded_line(torch, td, synth, MornaSearch, device, rank, world, args.sharded_rows,
                                                    max(5, min(args.steps, 10)), barrier, max_over_ranks)
         torch.cuda.empty_cache()
+        rs = extras["rows_sharded"]
+        rs["step_frac"] = rs["tensor_frac"]
+        roofline["step_frac_1M_rows"] = {
+            "value": rs["tensor_frac"], "n_gpus": world, "ms_per_step": rs["ms_per_step"],
+            "what": "the same whole-step fraction (2*Q*N*D flops / step time / GPUs / measured bf16 peak; thresholds, top-k, "
+                    "FP64 re-rank%s included) on north_star's target shape, %d x %d rows: the per-query costs of the "
+                    "exact answer (k-th selection, 100 x 12 KB of rows re-read in FP64) do not grow with N, the contraction does"
+                    % (" and the NCCL exchange" if world > 1 else "", args.sharded_rows, DIM)}
     note("rows-sharded done")
     single = index = None
     if rank == 0 and full:
