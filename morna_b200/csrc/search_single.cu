@@ -178,6 +178,7 @@ __device__ void select_candidates(const float *__restrict__ score, int64_t n, in
 // this -- after its share of the scan -- and its scan then runs under query j's selection tail (one CTA, ~7 us, 147 SMs
 // idle) and the launch gap.  Workspaces alternate between two halves: the wait BEFORE the trigger makes "kernel j+1
 // let kernel j+2 start" imply "kernel j has completed", so the half kernel j+2 reuses is free and zeroed again.
+__device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void chain_handoff() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -206,7 +207,11 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int chunks = (int)(ld >> 2);
     if (tid == 0) s_huge = 0;
-    if (blockIdx.x == 0 && tid == 0) ctl->stamp[0] = global_ns();
+    // hand-over 3: the next query's kernel may begin as soon as this one is resident; each kernel then waits for its
+    // predecessor just before its first write into the workspace (see chain_wait below)
+    if (chain == 3) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    bool must_wait = chain == 3;
+    if (blockIdx.x == 0 && tid == 0 && chain != 3) ctl->stamp[0] = global_ns();     // (debug stamp; a workspace write)
     if (prefetch_bytes > 0) {
         // The query staging and the qq sum below take ~3 us in which no row is read.  Pull the head of this warp's
         // first-pass rows into L2 meanwhile (no registers held): HBM starts streaming at once.  Measured at 21,504 x 3000
@@ -298,6 +303,7 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
             const double s = warp_sum(acc[u]);
             if (lane == u) mine = s;
         }
+        if (must_wait) { chain_wait(); must_wait = false; }           // (hand-over 3) the predecessor has completed: the workspace is ours
         if (lane < R) {
             const double d = angular_from_sums(my_pp, qq, mine);
             dist[r + lane] = d;
@@ -319,6 +325,7 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
             acc = fma(f32_scaled_f64(v.z), qb.x, acc); acc = fma(f32_scaled_f64(v.w), qb.y, acc);
         }
         acc = warp_sum(acc);
+        if (must_wait) { chain_wait(); must_wait = false; }
         if (lane == 0) {
             const double d = angular_from_sums(pp[r], qq, acc);
             dist[r] = d;
@@ -329,6 +336,7 @@ scan64_select_kernel(const float *__restrict__ vectors, const double *__restrict
         }
     }
     if (chain == 1 || (chain == 2 && row_end - row_begin <= R)) chain_handoff();
+    if (must_wait) { chain_wait(); must_wait = false; }               // warps without rows; the ticket below is a workspace write
     // last CTA to arrive answers the query from all keys
     __threadfence();
     __syncthreads();
@@ -566,7 +574,7 @@ extern "C" int morna_knn_single(const float *vectors, const double *pp, int64_t 
 
 static int g_single_chain = 2;      // morna_debug_set_tuning key 29: 0 = plain launches, 1 = hand over after the scan, 2 = after the first pass (measured
                                     // at 21,504 x 3000, scripts/single_chain_probe.py: 58.3 / 49.0 / 44.5 us per query)
-namespace morna { void set_single_chain(int v) { g_single_chain = v < 0 ? 0 : (v > 2 ? 2 : v); } }
+namespace morna { void set_single_chain(int v) { g_single_chain = v < 0 ? 0 : (v > 3 ? 3 : v); } }
 
 extern "C" int morna_knn_single_stream(const float *vectors, const double *pp, int64_t n, int32_t dim, int64_t ld,
                                        int32_t id_base, const double *queries, int64_t query_stride, int32_t n_queries,

@@ -26,7 +26,7 @@ def main():
     want_i, want_d = torch.stack(want_i), torch.stack(want_d)
     side = torch.cuda.Stream(device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for chain in (0, 1, 2, 1, 0):
+    for chain in (0, 1, 2, 3, 2, 3):
         lib.morna_debug_set_tuning(29, chain)
         with torch.cuda.stream(side):
             ids, d = srch.single_search_stream(Q, k)

@@ -438,7 +438,7 @@ def _run_single_query_checks(n, d, k):
     check_topk(true_d, s_ids[0].cpu().numpy()[:m], s_d[0].cpu().numpy()[:m], tol=1e-9)
 
 
-@pytest.mark.parametrize("chain", [0, 1, 2])
+@pytest.mark.parametrize("chain", [0, 1, 2, 3])
 def test_single_query_stream_equals_one_query_at_a_time(chain):
     """morna_knn_single_stream (back-to-back kernels, programmatic dependent launch, alternating workspaces) returns for
     every query what morna_knn_single returns, which is pinned to the oracle above -- including queries that fall
