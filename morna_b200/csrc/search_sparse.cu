@@ -228,8 +228,13 @@ select_radix_kernel(const double *__restrict__ dist, int64_t n, int64_t dist_ld,
     // keys are compared under `mask` from here on: either all 64 bits, or the prefix of a bin that is wanted whole
     const unsigned long long key_k = s_prefix;                         // the kk-th smallest key (under mask)
     const int quota = s_need;                                          // how many of the rows tied with it (under mask) belong to the answer
-    // descending row order: everything below key_k, and the first `quota` ties met
-    for (int64_t top = n; top > 0; top -= kRsThreads) {
+    // descending row order: everything below key_k, and the first `quota` ties met.  While ties are still wanted every
+    // 1024-row step ranks its ties across the CTA (two barriers); thousands of rows tie in a sparse index, so the quota is
+    // met within a step or two, and from then on only the (fewer than k) rows below key_k matter: no barriers, four
+    // loads in flight.  (ncu of the one-loop version: half of the kernel's samples sat in the per-step prefix over the
+    // 32 warp totals, executed for all 49 steps.)
+    int64_t top = n;
+    for (; top > 0 && s_ties < quota; top -= kRsThreads) {             // (s_ties is read between the barriers that follow its update)
         const int64_t i = top - 1 - tid;
         bool less = false, tie = false;
         double d = 0.0;
@@ -257,6 +262,29 @@ select_radix_kernel(const double *__restrict__ dist, int64_t n, int64_t dist_ld,
         if (tid == 0) s_ties += block_ties;
         __syncthreads();
     }
+    for (; top > 0; top -= kUnroll * kRsThreads) {                     // the quota of ties is met: rows below key_k only
+        double d[kUnroll];
+        int64_t i[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            i[u] = top - 1 - (int64_t)u * kRsThreads - tid;
+            d[u] = i[u] >= 0 ? row[i[u]] : INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const bool take = i[u] >= 0 && ((unsigned long long)__double_as_longlong(d[u]) & mask) < key_k;
+            const unsigned int take_mask = __ballot_sync(kFull, take);
+            if (take_mask == 0u) continue;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_count, __popc(take_mask));
+            base = __shfl_sync(kFull, base, 0);
+            if (take) {
+                const int at = base + __popc(take_mask & ((1u << lane) - 1u));
+                if (at < kRsMaxK) { sd[at] = d[u]; si[at] = id_base + (int)i[u]; }
+            }
+        }
+    }
+    __syncthreads();
     const int count = min(s_count, kRsMaxK);                           // == kk
     int P = 32;
     while (P < count) P <<= 1;
