@@ -1832,7 +1832,7 @@ extern "C" int morna_debug_tensor_scores(const void *hs, int64_t ld_h, const flo
 
 /* Experiment knobs, process-wide: key 0 = GEMM variant (1 CTA pairs / 0 single CTA),
  * key 1 = shared-memory pipeline stages of the pair variant (4 or 6). */
-namespace morna { void set_single_tma(int v); void set_acc_pipelined(int v); void set_acc_split(int v); void set_acc_variant(int v); void set_acc_shift(int v); void set_ids_early_exit(int v); void set_single_prefetch(int v); void set_single_prefetch_rows(int v); void set_single_chain(int v); }
+namespace morna { void set_single_tma(int v); void set_acc_pipelined(int v); void set_acc_split(int v); void set_acc_variant(int v); void set_acc_shift(int v); void set_ids_early_exit(int v); void set_single_prefetch(int v); void set_single_prefetch_rows(int v); void set_single_chain(int v); void set_sparse_tile_mb(int v); }
 
 /* Experiment hook: device buffer of gridDim.x * 4 int64 that the pair GEMM's MMA thread fills with its wait cycles (NULL = off). */
 extern "C" int morna_debug_gemm_counters(void *buffer) { g_gemm_debug = (long long *)buffer; return MORNA_OK; }
@@ -1854,6 +1854,7 @@ extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
     else if (key == 27) morna::set_single_prefetch(value);
     else if (key == 28) morna::set_single_prefetch_rows(value);
     else if (key == 29) morna::set_single_chain(value);
+    else if (key == 35) morna::set_sparse_tile_mb(value);
     else if (key == 6) g_rerank_phase_mb = value;
     else if (key == 14) g_rerank_kernel = value;
     else if (key == 15) g_rerank_ctas = value;

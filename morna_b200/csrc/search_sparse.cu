@@ -310,13 +310,21 @@ select_radix_kernel(const double *__restrict__ dist, int64_t n, int64_t dist_ld,
     }
 }
 
+static int g_sparse_tile_mb = 1700;      // morna_debug_set_tuning key 35: MB of distance scratch per query tile
+void set_sparse_tile_mb(int v) { g_sparse_tile_mb = v > 0 ? v : 1700; }
+
 static int64_t sparse_query_tile(int64_t n, int64_t nq) {
-    const int64_t budget = (int64_t)96 << 20;    // bytes of distance scratch per tile: the selection's seven passes hit in L2
+    // Bytes of distance scratch per tile.  Measured at 50,000 rows x 4096 queries (scripts/sparse_probe.py, fixture-like /
+    // 40-junction rows): 96 MB (251 queries, the passes hit in L2) 4.21 / 5.72 ms, 240 MB 3.35 / 4.43, 480 MB 3.07 / 4.00,
+    // 960 MB 2.88 / 3.74, all queries in one tile (1.64 GB) 2.79 / 3.62 -- the selection kernel (one 1024-thread CTA per
+    // query, two per SM) wants many waves per launch more than it wants L2 hits.  Several tiles are made equal.
+    const int64_t budget = (int64_t)g_sparse_tile_mb << 20;
     int64_t t = budget / (8 * (n > 0 ? n : 1));
     if (t < 1) t = 1;
     if (t > 16384) t = 16384;
-    if (t > nq) t = nq;
-    return t > 0 ? t : 1;
+    if (t >= nq) return nq > 0 ? nq : 1;
+    const int64_t tiles = (nq + t - 1) / t;
+    return (nq + tiles - 1) / tiles;
 }
 
 }  // namespace morna
