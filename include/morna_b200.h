@@ -121,7 +121,9 @@ int morna_tokenize_fill(const char *text, size_t nbytes, int32_t n_threads, uint
  * barrier-per-row path with the same results.
  * The accumulator is bucket-major: acc[b * acc_ld + (internal_id - id_lo)], and
  * only internal ids in [id_lo, id_hi) are accumulated (multi-GPU shards by id
- * range, each rank streaming the same rows).  The call zero-fills acc itself.
+ * range, each rank streaming the same rows).  The call writes every cell [0, id_hi - id_lo) of every
+ * column (zeros where nothing was added; id_of_sample must map onto every id of the range, as
+ * morna_assign_internal_ids' output does); cells at or beyond id_hi - id_lo are not touched.
  *   bucket/sign/idf  [dev] per-row, from morna_hash_junctions / morna_idf_host
  *   cov              [dev] int32[nnz] coverages
  *   id_of_sample     [dev] int32[max_sample_id + 1] from morna_assign_internal_ids
