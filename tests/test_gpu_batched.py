@@ -417,6 +417,32 @@ def test_sparse_exact_path_is_bit_identical_on_the_reference_fixture():
     assert np.array_equal(got[0][0], w_i.cpu().numpy()) and np.array_equal(got[0][1], w_d.cpu().numpy())
 
 
+@pytest.mark.parametrize("tile_mb", [1, 3, 1700])
+def test_sparse_exact_path_query_tiles_of_any_size_agree(tile_mb):
+    """The CSR exact path walks the queries in tiles sized by its distance scratch (one tile by default since the last
+    session of round 2): many small tiles (unequal last tile included), a few, and one give the same ids and distances
+    as the dense scan -- tie-heavy fixture rows, so the selection's tie-ranking and barrier-free phases both run."""
+    from morna_b200 import _lib
+    lib = _lib.load()
+    oracle = mo.go_index(tiny_lines(), features=3000, sample_threshold=100)
+    S = oracle.matrix_f32()
+    srch = make_search(S)
+    assert srch.csr is not None
+    dense = _dense_twin(srch)
+    rng = np.random.default_rng(11)
+    Q = S[rng.permutation(S.shape[0])[:173]].astype(np.float64)
+    Q[5:9] += 0.02 * rng.standard_normal((4, 3000))
+    q = torch.from_numpy(Q).cuda()
+    try:
+        assert lib.morna_debug_set_tuning(35, tile_mb) == 0
+        for k in (7, 100):
+            s_ids, s_d = srch.exact_search_device(q, k)
+            d_ids, d_d = dense.exact_search_device(q, k, allow_single=False)
+            assert torch.equal(s_ids, d_ids) and torch.equal(s_d, d_d)
+    finally:
+        lib.morna_debug_set_tuning(35, 1700)
+
+
 @pytest.mark.parametrize("n,d,max_nnz", [(5000, 3000, 3), (3000, 130, 16), (2000, 7, 4), (4000, 40000, 8)])
 def test_sparse_exact_path_matches_dense_kernels_bit_for_bit(n, d, max_nnz):
     """Synthetic sparse rows with up to 16 non-zeros (several per summation lane, negative zeros, float32 denormals,
