@@ -343,7 +343,8 @@ int morna_debug_tensor_scores(const void *hs, int64_t ld_h, const float *rho_max
  *   17 side jobs: 0 = helper warps off (resume calls then re-rank everything)
  *   29 single-query stream: 0 = plain launches, 1 = next query starts after the scan, 2 = after the first row pass (default),
  *      3 = at once (each kernel waits for its predecessor before its first workspace write; measured equal to 2)
- *   35 sparse exact path: MB of distance scratch per query tile (default 1700) */
+ *   35 sparse exact path: MB of distance scratch per query tile (default 1700)
+ *   36 batched: growth factor of the row blocks after the first (default 1 = equal blocks of key 9's size) */
 int morna_debug_set_tuning(int32_t key, int32_t value);
 /* Experiment hook: [dev] int64[grid * 4] that the pair GEMM's MMA-issuing thread fills with the cycles it spent waiting for
  * operand tiles (TMA) and for a free accumulator (epilogue), and its total; NULL switches it off (default). */

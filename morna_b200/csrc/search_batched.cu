@@ -1239,6 +1239,8 @@ static int g_gemm_pair = 1;       // 1: CTA pairs (cta_group::2), 0: single CTAs
 static int g_gemm_stages = 4;
 static int g_block_rows = 131072;  // rows scored between two refinements of the candidate lists (key 9)
 static int g_pilot_rows = kKthMax; // rows of the pilot block whose scores are dumped for the first thresholds (key 10)
+static int g_block_growth = 1;     // key 36: factor by which the blocks after the first grow (1 = equal blocks, the default: doubling saves
+                                   // four refinements at 1 M rows but measured within the run-to-run noise, profiles/r02_block_rows_sweep.log)
 static int g_first_block = 0;      // rows up to the first refinement (key 11); 0 = g_block_rows
 static int g_rerank_ctas_per_sm = 0; // key 13: cap on resident re-rank CTAs per SM (0 = whatever fits)
 static int g_rerank_rows = 4;     // candidate rows per warp pass of the re-rank (2, 4, 8; 16 for the warp kernel)
@@ -1466,8 +1468,12 @@ static int score_impl(const void *hs, int64_t ld_h, const float *rho_max, int64_
     mark();                                                      // 3: thresholds
     // the rest in blocks of g_block_rows rows: keep scores above thr; between blocks thr is tightened to the
     // k-th best seen so far and the lists are compacted, so a later block adds ~k entries per query, not ~N/n0 * k
+    // (key 36 lets the blocks grow geometrically: after the first refinement a query's threshold passes ~k/rows_seen of the
+    // rows, so a block as large as everything seen so far adds about k entries to its list; off by default)
+    int64_t step = g_block_rows;
     for (int64_t b0 = w.n0; b0 < n;) {
-        int64_t b1 = b0 == w.n0 ? (int64_t)(g_first_block > 0 ? g_first_block : g_block_rows) : b0 + g_block_rows;
+        int64_t b1 = b0 == w.n0 ? (int64_t)(g_first_block > 0 ? g_first_block : g_block_rows) : b0 + step;
+        if (b0 != w.n0 && g_block_growth > 1) step *= g_block_growth;
         if (b1 > n || b1 <= b0) b1 = n;
         rc = launch_gemm((int32_t)b0, (int32_t)b1, 1);
         if (rc != MORNA_OK) return rc;
@@ -1511,9 +1517,11 @@ extern "C" int morna_knn_batched_score(const void *hs, int64_t ld_h, const float
 namespace morna {
 // which of the two first-pass list buffers is current after a scoring call: one swap per refinement between row blocks
 static int list_swaps(int64_t n, const BatchWs &w) {
-    int swaps = 0;
+    int swaps = 0;                                               // (the same walk as score_impl's block loop)
+    int64_t step = g_block_rows;
     for (int64_t b0 = w.n0; b0 < n;) {
-        int64_t b1 = b0 == w.n0 ? (int64_t)(g_first_block > 0 ? g_first_block : g_block_rows) : b0 + g_block_rows;
+        int64_t b1 = b0 == w.n0 ? (int64_t)(g_first_block > 0 ? g_first_block : g_block_rows) : b0 + step;
+        if (b0 != w.n0 && g_block_growth > 1) step *= g_block_growth;
         if (b1 > n || b1 <= b0) b1 = n;
         b0 = b1;
         if (b0 < n) ++swaps;
@@ -1855,6 +1863,7 @@ extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
     else if (key == 28) morna::set_single_prefetch_rows(value);
     else if (key == 29) morna::set_single_chain(value);
     else if (key == 35) morna::set_sparse_tile_mb(value);
+    else if (key == 36) g_block_growth = value >= 1 && value <= 8 ? value : 1;
     else if (key == 6) g_rerank_phase_mb = value;
     else if (key == 14) g_rerank_kernel = value;
     else if (key == 15) g_rerank_ctas = value;

@@ -27,8 +27,8 @@ srch.enable_tensor_path()
 q = synth.gauss(Q, D, dev, 99).to(torch.float64)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ref = None
-for block, first in ((131072, 0), (262144, 0), (524288, 0), (1 << 20, 0), (262144, 32768), (524288, 32768), (1 << 20, 32768), (1 << 20, 65536), (131072, 0)):
-    lib.morna_debug_set_tuning(9, block); lib.morna_debug_set_tuning(11, first)
+for block, first, growth in ((131072, 0, 1), (131072, 0, 2), (131072, 0, 4), (65536, 0, 2), (131072, 0, 1), (131072, 0, 2)):
+    lib.morna_debug_set_tuning(9, block); lib.morna_debug_set_tuning(11, first); lib.morna_debug_set_tuning(36, growth)
     for _ in range(2):
         ids, d = mdist.sharded_batched_search(srch, q, K, check_overflow=False)
     torch.cuda.synchronize()
@@ -40,6 +40,6 @@ for block, first in ((131072, 0), (262144, 0), (524288, 0), (1 << 20, 0), (26214
     if ref is None:
         ref = (ids.clone(), d.clone())
     same = torch.equal(ids, ref[0]) and torch.equal(d, ref[1])
-    print("block %8d first %6d: %.2f ms per step, step fraction %.3f, same=%s"
-          % (block, first, ms, 2.0 * Q * N * D / (ms * 1e-3) / 1e12 / peak, same), flush=True)
-lib.morna_debug_set_tuning(9, 131072); lib.morna_debug_set_tuning(11, 0)
+    print("block %8d first %6d growth %d: %.2f ms per step, step fraction %.3f, same=%s"
+          % (block, first, growth, ms, 2.0 * Q * N * D / (ms * 1e-3) / 1e12 / peak, same), flush=True)
+lib.morna_debug_set_tuning(9, 131072); lib.morna_debug_set_tuning(11, 0); lib.morna_debug_set_tuning(36, 1)
