@@ -464,7 +464,8 @@ row_segments_kernel(const int64_t *__restrict__ row_off, const int8_t *__restric
     const int32_t n_pass = bucket_begin[dim];                  // rows under the threshold sort past the last bucket
     const int64_t total = (int64_t)n_pass * (n_ranges + 1);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / (n_ranges + 1);
+        // (32-bit division when the index fits: a 64-bit divide is a hundred instructions on this path)
+        const int64_t r = total <= 0xffffffffll ? (int64_t)((uint32_t)i / (uint32_t)(n_ranges + 1)) : i / (n_ranges + 1);
         const int32_t q = (int32_t)(i - r * (n_ranges + 1));
         const int32_t j = rows_by_bucket[r];
         const int64_t b = row_off[j];
@@ -472,8 +473,29 @@ row_segments_kernel(const int64_t *__restrict__ row_off, const int8_t *__restric
         if (q == 0) { meta[r].pos = b; meta[r].w = (double)sign[j] * idf[j]; }
         int32_t lo = 0, hi = n;                                // first p in [0, n] with sample[b + p] >= q << shift
         if (q == n_ranges) lo = n;
-        else if (q > 0) {
+        else if (q > 0 && n > 0) {
             const int32_t bound = q << shift;
+            // The ids of a row are spread over [first, last] roughly evenly: start next to the interpolated position and
+            // gallop outwards (a few probes in one or two cache lines instead of log2(n) scattered ones), then bisect the
+            // bracket.  Any ascending row gives the same answer as a plain binary search.
+            const int32_t first = __ldg(sample + b), last = __ldg(sample + b + n - 1);
+            if (bound <= first) hi = 0;
+            else if (bound > last) lo = n;
+            else {
+                int32_t g = (int32_t)((float)(bound - first) * (float)(n - 1) / (float)max(last - first, 1));   // (a guess: float is enough)
+                g = min(max(g, 0), n - 1);
+                if (__ldg(sample + b + g) < bound) {           // answer is to the right of g
+                    lo = g + 1;
+                    int32_t stepw = 4;
+                    while (lo + stepw < n && __ldg(sample + b + lo + stepw - 1) < bound) { lo += stepw; stepw <<= 1; }
+                    hi = min(n, lo + stepw);
+                } else {                                       // sample[g] >= bound: answer is at or left of g
+                    hi = g;
+                    int32_t stepw = 4;
+                    while (hi - stepw > 0 && __ldg(sample + b + hi - stepw) >= bound) { hi -= stepw; stepw <<= 1; }
+                    lo = max(0, hi - stepw);
+                }
+            }
             while (lo < hi) {
                 const int32_t mid = (lo + hi) >> 1;
                 if (__ldg(sample + b + mid) < bound) lo = mid + 1; else hi = mid;
@@ -497,7 +519,7 @@ chunk_count_kernel(const int32_t *__restrict__ not_ascending, const int32_t *__r
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n_rows_cap * n_ranges; i += (int64_t)gridDim.x * blockDim.x) {
         int32_t c = 0;
         if (i < total) {
-            const int64_t p = i / n_pass, r = i - p * n_pass;
+            const int64_t p = total <= 0xffffffffll ? (int64_t)((uint32_t)i / (uint32_t)n_pass) : i / n_pass, r = i - p * n_pass;
             const int32_t *sg = seg + r * (n_ranges + 1) + p;
             c = (max(sg[1] - sg[0], 0) + 31) >> 5;
         }
@@ -513,7 +535,7 @@ chunk_fill_kernel(const int32_t *__restrict__ not_ascending, const int32_t *__re
     const int64_t n_pass = bucket_begin[dim];
     const int64_t total = n_pass * n_ranges;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t p = i / n_pass, r = i - p * n_pass;
+        const int64_t p = total <= 0xffffffffll ? (int64_t)((uint32_t)i / (uint32_t)n_pass) : i / n_pass, r = i - p * n_pass;
         const int32_t *sg = seg + r * (n_ranges + 1) + p;
         const int32_t lo = sg[0], n = max(sg[1] - lo, 0);
         if (n == 0) continue;
