@@ -1068,6 +1068,7 @@ kth_warp_kernel(KthParams p, int nq) {
         // stream: lane owns float4 groups lane, lane+32, ...; survivors go to its private list
         const int groups = (count + 3) >> 2;
         bool overflowed = false;
+        const float pivot_f = pivot ? key_float(pivot) : -INFINITY;
         constexpr int kInFlight = 8;                                         // 16-byte loads in flight per lane (the stream is latency bound)
         for (int g0 = lane; g0 < groups; g0 += 32 * kInFlight) {
             float4 v[kInFlight];
@@ -1083,12 +1084,16 @@ kth_warp_kernel(KthParams p, int nq) {
                 const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    const int idx = 4 * g + t;
-                    const uint32_t key = float_key(vv[t]);
-                    if (idx < count && key >= pivot) {
-                        if (mine < kKwSlots) { lkey[mine * 32 + lane] = key; lidx[mine * 32 + lane] = (uint16_t)idx; }
-                        else overflowed = true;
-                        ++mine;
+                    // a float compare first: key order refines float order (only -0 < +0 differs), so v >= pivot_f holds for
+                    // every entry whose key reaches the pivot; the few per cent that pass are then tested exactly
+                    if (vv[t] >= pivot_f) {
+                        const int idx = 4 * g + t;
+                        const uint32_t key = float_key(vv[t]);
+                        if (idx < count && key >= pivot) {
+                            if (mine < kKwSlots) { lkey[mine * 32 + lane] = key; lidx[mine * 32 + lane] = (uint16_t)idx; }
+                            else overflowed = true;
+                            ++mine;
+                        }
                     }
                 }
             }
@@ -1165,10 +1170,43 @@ kth_warp_kernel(KthParams p, int nq) {
     };
     if (lists_ok && cut_key >= pivot) {              // every entry >= cut sits in the lane lists
         const int most = __reduce_max_sync(kFull, mine);
-        for (int j = 0; j < most; ++j) {
-            const bool have = j < mine;
-            const uint32_t key = have ? lkey[j * 32 + lane] : 0u;
-            emit(have && key >= cut_key, key_float(key), have ? (int)lidx[j * 32 + lane] : 0);
+        if (kPilot) {
+            for (int j = 0; j < most; ++j) {
+                const bool have = j < mine;
+                const uint32_t key = have ? lkey[j * 32 + lane] : 0u;
+                emit(have && key >= cut_key, key_float(key), have ? (int)lidx[j * 32 + lane] : 0);
+            }
+        } else {
+            // the emitted entry's row id is read from the candidate list: four steps' loads are issued before their stores
+            // (one step at a time, every store waited for its own load: half of the final pass's stall samples in ncu)
+            const int32_t *ids_in = p.cand_id + (int64_t)q * p.cap;
+            for (int j0 = 0; j0 < most; j0 += 4) {
+                bool keep[4];
+                uint32_t key[4];
+                int32_t id[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u;
+                    const bool have = j < mine;
+                    key[u] = have ? lkey[j * 32 + lane] : 0u;
+                    keep[u] = have && key[u] >= cut_key;
+                    id[u] = keep[u] ? ids_in[lidx[j * 32 + lane]] : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned mask = __ballot_sync(kFull, keep[u]);
+                    const int at = out + __popc(mask & ((1u << lane) - 1u));
+                    if (keep[u] && at < out_cap) {
+                        if (kRefine) {
+                            p.cand2_score[(int64_t)q * p.cap + at] = key_float(key[u]);
+                            p.cand2_id[(int64_t)q * p.cap + at] = id[u];
+                        } else {
+                            p.fin_id[(int64_t)q * p.fcap + at] = id[u];
+                        }
+                    }
+                    out += __popc(mask);
+                }
+            }
         }
     } else {
         for (int i0 = 0; i0 < count; i0 += 32) {
