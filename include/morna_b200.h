@@ -343,6 +343,7 @@ int morna_debug_tensor_scores(const void *hs, int64_t ld_h, const float *rho_max
  *   17 side jobs: 0 = helper warps off (resume calls then re-rank everything)
  *   29 single-query stream: 0 = plain launches, 1 = next query starts after the scan, 2 = after the first row pass (default),
  *      3 = at once (each kernel waits for its predecessor before its first workspace write; measured equal to 2)
+ *   34 re-rank: 1 = each query's candidates walked in ascending row order (default), 0 = emission order
  *   35 sparse exact path: MB of distance scratch per query tile (default 1700)
  *   36 batched: growth factor of the row blocks after the first (default 1 = equal blocks of key 9's size) */
 int morna_debug_set_tuning(int32_t key, int32_t value);

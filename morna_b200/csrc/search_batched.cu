@@ -164,6 +164,7 @@ struct RerankParams {
     const double *queries; int64_t q_ld; const double *qq;
     const int32_t *fin_id; const int32_t *fin_cnt; const uint8_t *overflow;
     int32_t fcap, nq, phases, phase_rows;
+    int32_t sort_rows;              // key 34: candidates of a query walked in ascending row order (L2 reuse across queries)
     int32_t rows_evict_first;       // key 32: L2 policy of the candidate-row loads (0 evict_normal = default, 1 evict_first, 2 evict_last, 3 mixed, 4 no hint)
     double *fin_dist;
     unsigned long long *queue;      // warp kernel: next item; zero when the batch's lists are complete
@@ -244,6 +245,27 @@ __device__ __forceinline__ void rerank_dist_body(const RerankParams &p) {
         group_sync();
         const int m = s_count;
         if (m == 0) continue;
+        if (p.sort_rows && m <= 256 && (size_t)p.ld * sizeof(double) >= 3 * 256 * sizeof(int)) {
+            // Walk the candidates in ascending row order (key 34): the CTAs that run side by side then sweep the matrix
+            // roughly together and more of the rows listed by several queries are still in L2 when the next one asks
+            // (ncu at the headline shape: L2 hit rate 30.7 -> 37.4 %, DRAM reads 3.91 -> 3.38 GB, 723 -> 696 us; the sweep
+            // is loose -- the i-th smallest of ~118 random row ids varies by +-2300 rows between queries -- so most rows
+            // still come from HBM).  Rank by counting in the still unused query staging area; results do not depend on
+            // the order of the walk.
+            int *key = reinterpret_cast<int *>(qs), *sorted = key + 256;
+            if (tid < m) key[tid] = ids[list[tid]];
+            if (tid + kRrThreads < m) key[tid + kRrThreads] = ids[list[tid + kRrThreads]];
+            group_sync();
+            for (int i = tid; i < m; i += kRrThreads) {
+                const int mine = key[i];
+                int rank = 0;
+                for (int j = 0; j < m; ++j) { const int o = key[j]; rank += (o < mine) | ((o == mine) & (j < i)); }
+                sorted[rank] = list[i];
+            }
+            group_sync();
+            for (int i = tid; i < m; i += kRrThreads) list[i] = sorted[i];
+            group_sync();
+        }
         {
             const double *qsrc = p.queries + (int64_t)q * p.q_ld;
             if ((p.q_ld & 1) == 0 && (p.dim & 1) == 0) {
@@ -1288,6 +1310,7 @@ static int g_rerank_ctas = 0;      // key 15: CTAs per SM of the warp kernel (0 
 static int g_rerank_subs = 0;      // key 16: items per query of the unsplit warp re-rank (0 = 4)
 static int g_side_job = 0;         // key 17: 1 = side jobs on: helper warps in the GEMM kernel re-rank the previous batch (measured slower:
                                    // the GEMM's TMA stream and the helpers' gathers queue behind each other)
+static int g_rerank_sort_rows = 1;     // key 34: candidates walked in ascending row order (ncu: 3.91 -> 3.38 GB DRAM, 723 -> 696 us)
 static int g_rerank_evict_first = 0;   // key 32 (measured, scripts/rerank_policy_sweep.py: an explicit evict_normal hint is 1-4 % faster than none)
 static int g_gemm_l2_keep = 0;         // key 33
 static int g_rerank_fat_sms = 0;   // key 30: > 0 = the re-rank runs as this many SM-filling CTAs ...
@@ -1738,6 +1761,7 @@ static int make_rerank_params(RerankParams &rp, bool &warp_kernel, const float *
     rp.fcap = kFinCap; rp.nq = (int32_t)nq; rp.fin_dist = (double *)(ws + w.fin_dist);
     rp.queue = (unsigned long long *)(ws + w.queue);
     rp.rows_evict_first = g_rerank_evict_first;
+    rp.sort_rows = g_rerank_sort_rows;
     // phases: only when a row is re-ranked several times per batch (otherwise every row is read at
     // most about once and splitting would only re-read the queries)
     rp.phases = 1; rp.phase_rows = (int32_t)n; rp.subs = 1;
@@ -1910,6 +1934,7 @@ extern "C" int morna_debug_set_tuning(int32_t key, int32_t value) {
     else if (key == 18) g_rerank_pipe = value;
     else if (key == 32) g_rerank_evict_first = value >= 0 && value <= 4 ? value : 0;
     else if (key == 33) g_gemm_l2_keep = value ? 1 : 0;
+    else if (key == 34) g_rerank_sort_rows = value ? 1 : 0;
     else if (key == 30) g_rerank_fat_sms = value > 0 ? value : 0;
     else if (key == 31) g_gemm_pairs_cap = value > 0 ? value : 0;
     else if (key == 19) g_carveout_hint = value;

@@ -9,6 +9,8 @@ lib = _lib.load()
 kern = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 rows_per = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 phase_mb = int(sys.argv[3]) if len(sys.argv) > 3 else -1
+if len(sys.argv) > 4:
+    lib.morna_debug_set_tuning(34, int(sys.argv[4])); lib.morna_debug_set_tuning(20, int(sys.argv[5]) if len(sys.argv) > 5 else 1)
 N, D, Q, K = 50000, 3000, 4096, 100
 S = synth.gauss(N, D, "cuda")
 s = MornaSearch(vectors=S, stats=(N, N, D))
