@@ -1012,8 +1012,17 @@ struct KthParams {
 // key of the kk-th largest of the keys one warp holds in registers (kItems per lane; 0 = padding)
 template <int kItems>
 __device__ __forceinline__ uint32_t warp_kth_largest(const uint32_t (&key)[kItems], int kk) {
-    uint32_t best = 0;
-    for (int bit = 31; bit >= 0; --bit) {
+    // every real key lies between the smallest non-zero and the largest key the warp holds, so the answer shares their
+    // common leading bits: the bisection starts below them (scores of one query differ in ~23 of their 32 key bits)
+    uint32_t hi = 0u, lo = ~0u;
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) { hi = max(hi, key[j]); lo = min(lo, key[j] ? key[j] : ~0u); }
+    hi = __reduce_max_sync(kFull, hi);
+    lo = __reduce_min_sync(kFull, lo);
+    if (hi == 0u || kk <= 0) return 0u;                       // nothing but padding
+    const int first = 31 - __clz((int)(hi ^ lo) | 1);         // highest bit in which two real keys can differ (bit 0 at least)
+    uint32_t best = first < 31 ? hi & ~((2u << first) - 1u) : 0u;
+    for (int bit = first; bit >= 0; --bit) {
         const uint32_t trial = best | (1u << bit);
         int c = 0;
 #pragma unroll
