@@ -1109,14 +1109,43 @@ kth_warp_kernel(KthParams p, int nq) {
                 v[u] = g < groups ? __ldcs(reinterpret_cast<const float4 *>(src + 4 * g))   // rows are 16-byte aligned and padded; read once
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            if (pivot != 0u) {
+                // With a pivot only a few per cent of the entries pass, but for almost every one of a lane's 32 entries SOME
+                // lane of the warp has a survivor, so a branch per entry makes the whole warp walk the insertion code 32
+                // times per step (ncu: two thirds of the pilot pass's instructions).  Instead: a bit per entry from a float
+                // compare (key order refines float order -- only -0 < +0 differs -- so v >= pivot_f holds for every entry
+                // whose key reaches the pivot), then a loop over the set bits, as long as the busiest lane's count (~5).
+                // The value is read again by index: registers cannot be indexed, the line is in L1/L2.
+                uint32_t bits = 0u;
+#pragma unroll
+                for (int u = 0; u < kInFlight; ++u) {
+                    bits |= (v[u].x >= pivot_f ? 1u : 0u) << (4 * u);
+                    bits |= (v[u].y >= pivot_f ? 1u : 0u) << (4 * u + 1);
+                    bits |= (v[u].z >= pivot_f ? 1u : 0u) << (4 * u + 2);
+                    bits |= (v[u].w >= pivot_f ? 1u : 0u) << (4 * u + 3);
+                }
+                while (bits) {
+                    const int e = __ffs((int)bits) - 1;
+                    bits &= bits - 1u;
+                    const int idx = 4 * (g0 + 32 * (e >> 2)) + (e & 3);
+                    if (idx < count) {
+                        const uint32_t key = float_key(src[idx]);
+                        if (key >= pivot) {
+                            if (mine < kKwSlots) { lkey[mine * 32 + lane] = key; lidx[mine * 32 + lane] = (uint16_t)idx; }
+                            else overflowed = true;
+                            ++mine;
+                        }
+                    }
+                }
+                continue;
+            }
 #pragma unroll
             for (int u = 0; u < kInFlight; ++u) {
                 const int g = g0 + 32 * u;
                 const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    // a float compare first: key order refines float order (only -0 < +0 differs), so v >= pivot_f holds for
-                    // every entry whose key reaches the pivot; the few per cent that pass are then tested exactly
+                    // (no pivot: every entry is a survivor)
                     if (vv[t] >= pivot_f) {
                         const int idx = 4 * g + t;
                         const uint32_t key = float_key(vv[t]);
