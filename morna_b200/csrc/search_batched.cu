@@ -1115,7 +1115,6 @@ kth_warp_kernel(KthParams p, int nq) {
                 // times per step (ncu: two thirds of the pilot pass's instructions).  Instead: a bit per entry from a float
                 // compare (key order refines float order -- only -0 < +0 differs -- so v >= pivot_f holds for every entry
                 // whose key reaches the pivot), then a loop over the set bits, as long as the busiest lane's count (~5).
-                // The value is read again by index: registers cannot be indexed, the line is in L1/L2.
                 uint32_t bits = 0u;
 #pragma unroll
                 for (int u = 0; u < kInFlight; ++u) {
@@ -1129,7 +1128,21 @@ kth_warp_kernel(KthParams p, int nq) {
                     bits &= bits - 1u;
                     const int idx = 4 * (g0 + 32 * (e >> 2)) + (e & 3);
                     if (idx < count) {
-                        const uint32_t key = float_key(src[idx]);
+                        // entry e of the 32 this lane holds: a select tree over the registers (31 selects; reading the
+                        // value again by index instead cost a DRAM / L2 round trip per survivor)
+                        float s16[16], s8[8], s4[4], s2[2];
+#pragma unroll
+                        for (int u = 0; u < kInFlight; ++u) {
+                            s16[2 * u] = (e & 1) ? v[u].y : v[u].x;
+                            s16[2 * u + 1] = (e & 1) ? v[u].w : v[u].z;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) s8[i] = (e & 2) ? s16[2 * i + 1] : s16[2 * i];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) s4[i] = (e & 4) ? s8[2 * i + 1] : s8[2 * i];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) s2[i] = (e & 8) ? s4[2 * i + 1] : s4[2 * i];
+                        const uint32_t key = float_key((e & 16) ? s2[1] : s2[0]);
                         if (key >= pivot) {
                             if (mine < kKwSlots) { lkey[mine * 32 + lane] = key; lidx[mine * 32 + lane] = (uint16_t)idx; }
                             else overflowed = true;
