@@ -235,3 +235,38 @@ def test_metadata_db_round_trip(tmp_path):
     meta.write_text("13\n")
     with pytest.raises(IndexError):
         files.write_meta(base, str(meta))
+
+
+# ------------------------------------------------------------------ bench.py contract (no GPU needed)
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` times the CPU port on the host cores and prints ONE JSON line with the keys the driver
+    reads (metric / unit / config of the GPU arm, impl, cpu_baseline of this run, e2e with zero copy bytes)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "queries/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("exact kNN queries/s") and "50000 samples x 3000 features" in line["config"]["workload"]
+    assert line["value"] > 0 and line["steps"] == 1 and line["n_gpus"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_gpu_arm_refuses_to_run_without_cuda():
+    """No CPU fallback: without a GPU the product arm of bench.py stops with an error instead of timing something else."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "3"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode != 0 and out.stdout.strip() == ""
+    assert "CUDA" in out.stderr or "cuda" in out.stderr
