@@ -470,6 +470,15 @@ def test_single_query_stream_equals_one_query_at_a_time(chain):
     assert torch.equal(i2, e2) and torch.equal(d2, f2)
     i3, _ = srch.single_search_stream(Qd[:0], k)
     assert i3.shape == (0, k)
+    if chain == 2:
+        # very wide --features: the staged query would not fit beside a second CTA, every query is flagged and the generic
+        # scan answers -- same lists
+        W = rng.standard_normal((300, 13000)).astype(np.float32)
+        wide = make_search(W)
+        wq = torch.from_numpy(np.concatenate([W[:2].astype(np.float64), rng.standard_normal((1, 13000))])).cuda()
+        i4, d4 = wide.single_search_stream(wq, 5)
+        e4, f4 = wide.exact_search_device(wq, 5, allow_single=False)
+        assert torch.equal(i4, e4) and torch.equal(d4, f4) and i4[0, 0] == 0 and i4[1, 0] == 1
 
 
 def test_single_query_ties_fall_back_and_shard_offsets():
